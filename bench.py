@@ -1,0 +1,323 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the surfel-rasteriser hot path.
+
+Workload (BASELINE.json configs[1]): 100k surfels, 512x512, 6 views, raster
+forward + backward per step, synthetic inputs.  One "step" is
+one pass of the hot path over that batch.
+
+  python bench.py --gpus N --steps K --warmup W            (our CUDA path)
+  python bench.py --impl reference ...                     (CPU reference arm:
+        the oracle port of the reference's rasteriser on all host cores)
+
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for the definition
+of every field.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+P_SURFELS, RES, VIEWS = 100000, 512, 6
+METRIC = "512^2 views/sec @100k Gaussians (surfel raster fwd+bwd)"
+UNIT = "views/s"
+CONFIG = {"workload": "C2: 100k surfels, 512x512, 6 views, raster fwd+bwd",
+          "surfels": P_SURFELS, "resolution": RES, "views_per_step": VIEWS,
+          "l2": "256 MiB L2 flush between timed steps (outside the timed events)",
+          "parallelism": "independent scenes per rank (no data-path collective)"}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def make_inputs(seed):
+    from tests.helpers import cameras, scene
+    g = scene(P_SURFELS, seed)
+    vs, ps, _, tf = cameras(VIEWS)
+    return g, vs, ps
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names)
+                   if any(len(r) >= 6 and r[2 + k].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference's rasteriser (all host threads)
+# ---------------------------------------------------------------------------
+def cpu_views_per_s(n_views, min_seconds, seed=40):
+    from oracle import surfel_oracle as so
+    from tests.helpers import oracle_view
+    g, vs, ps = make_inputs(seed)
+    rng = np.random.default_rng(0)
+    gc = rng.standard_normal((3, RES, RES)).astype(np.float32)
+    ga = rng.standard_normal((7, RES, RES)).astype(np.float32)
+    done, t0 = 0, time.perf_counter()
+    while True:
+        for v in range(n_views):
+            o = oracle_view(g, vs[v % VIEWS], ps[v % VIEWS], [1, 1, 1], RES, RES)
+            so.rasterize_backward(o, gc, ga)
+            done += 1
+        if time.perf_counter() - t0 >= min_seconds:
+            break
+    dt = time.perf_counter() - t0
+    return done / dt, done, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count()
+    for _ in range(args.warmup):
+        cpu_views_per_s(1, 0.0)
+    t0 = time.perf_counter()
+    total = 0
+    for _ in range(args.steps):
+        _, n, _ = cpu_views_per_s(VIEWS, 0.0)
+        total += n
+    dt = time.perf_counter() - t0
+    v = total / dt
+    out = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+           "data": "synthetic", "config": CONFIG,
+           "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                            "sample": "%d steps x %d views of the full C2 workload (oracle/surfel_oracle.c, OpenMP)"
+                                      % (args.steps, VIEWS)},
+           "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out))
+
+
+# ---------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    from gaussiananything_b200 import _lib, raster
+    from gaussiananything_b200.gs_surfel import GaussianRenderer2DGS
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.lib()
+    lib.ga_profile_enable.argtypes = [C.c_int]
+    lib.ga_profile_read.argtypes = [C.POINTER(C.c_float), C.c_int]
+    lib.ga_profile_read.restype = C.c_int
+
+    g, vs, ps = make_inputs(40 + rank)               # one independent scene per rank
+    B, P, V, H, W = 1, P_SURFELS, VIEWS, RES, RES
+    g13 = torch.tensor(g, device=dev)[None].contiguous()
+    vm = torch.tensor(vs, device=dev).reshape(B * V, 16).contiguous()
+    pm = torch.tensor(ps, device=dev).reshape(B * V, 16).contiguous()
+    bg = torch.ones(3, device=dev)
+    torch.manual_seed(rank)
+    d_color = torch.randn(B, V, 3, H, W, device=dev)
+    d_allmap = torch.randn(B, V, 7, H, W, device=dev)
+
+    # size the workspace once (like a training loop would), outside the timed region
+    _, _, _, st = raster.forward_raw(g13, vm.view(B, V, 4, 4), pm.view(B, V, 4, 4), bg, H, W)
+    D = st["num_rendered"]
+    max_inst = int(D * 1.25) + 1024
+    L = raster.layout(B, P, V, H, W, max_inst)
+    ws = torch.empty(L.total_bytes, device=dev, dtype=torch.uint8)
+    color = torch.empty(B, V, 3, H, W, device=dev)
+    allmap = torch.empty(B, V, 7, H, W, device=dev)
+    radii = torch.empty(B, V, P, device=dev, dtype=torch.int32)
+    nscr = lib.ga_raster_backward_scratch_bytes(B, P, V)
+    scratch = torch.empty(nscr, device=dev, dtype=torch.uint8)
+    grad = torch.empty(B, P, 13, device=dev)
+    flush = torch.empty(256 << 20, device=dev, dtype=torch.uint8)
+    stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    p = lambda t: C.c_void_p(t.data_ptr())
+
+    def step_device():
+        rc = lib.ga_raster_forward(p(g13), B, P, V, p(vm), p(pm), p(bg), H, W, 1.0, p(color), p(allmap),
+                                   p(radii), p(ws), L.total_bytes, max_inst, stream)
+        assert rc == 0, rc
+        rc = lib.ga_raster_backward(p(g13), B, P, V, p(vm), p(pm), p(bg), H, W, 1.0, p(radii), p(d_color),
+                                    p(d_allmap), p(ws), L.total_bytes, max_inst, p(scratch), nscr, p(grad),
+                                    stream)
+        assert rc == 0, rc
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- device-resident throughput ("value") + per-stage timing (roofline)
+    for _ in range(max(args.warmup, 3)):
+        flush.zero_()
+        step_device()
+    torch.cuda.synchronize(dev)
+    lib.ga_profile_enable(1)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    stage_ms = np.zeros(8)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    wall0 = time.perf_counter()
+    for k in range(args.steps):
+        flush.zero_()                               # L2 flush, outside the event pair
+        ev[k][0].record()
+        step_device()
+        ev[k][1].record()
+        ev[k][1].synchronize()
+        buf = (C.c_float * 8)()
+        n = lib.ga_profile_read(buf, 8)
+        stage_ms[:n] += np.array(buf[:n])
+    barrier()
+    wall = time.perf_counter() - wall0
+    lib.ga_profile_enable(0)
+    clocks = sampler.stop() if rank == 0 else None
+    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+    status = ws[L.status:L.status + 64].view(torch.int32).cpu()
+    assert int(status[1]) == 0, "workspace overflow inside the timed region"
+    assert torch.isfinite(grad).all()
+    t = torch.tensor([dev_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms_max = float(t.item())
+    value = world * V * args.steps / (dev_ms_max * 1e-3)
+    stage_ms /= args.steps
+
+    # ---- end-to-end through the public API with host buffers ("e2e")
+    rnd = GaussianRenderer2DGS(RES, 3, {})
+    h_g = torch.tensor(g)[None].pin_memory()
+    h_vm = torch.tensor(vs)[None].pin_memory()
+    h_pm = torch.tensor(ps)[None].pin_memory()
+    h_pos = torch.zeros(1, V, 3).pin_memory()
+    h_target = torch.rand(1, V, 3, H, W).pin_memory()
+    h2d = sum(x.numel() * x.element_size() for x in (h_g, h_vm, h_pm, h_pos, h_target))
+    d2h = 4 + P * 13 * 4
+
+    def step_e2e():
+        gg = h_g.to(dev, non_blocking=True).requires_grad_(True)
+        cv, cvp = h_vm.to(dev, non_blocking=True), h_pm.to(dev, non_blocking=True)
+        cp, tgt = h_pos.to(dev, non_blocking=True), h_target.to(dev, non_blocking=True)
+        out = rnd.render(gg, cv, cvp, cp, 0.36)
+        loss = ((out["image"] - tgt) ** 2).mean() + 0.1 * out["dist"].mean() + 0.05 * (1 - out["alpha"]).mean() \
+            + 0.01 * out["depth"].mean() + 0.01 * out["rend_normal"].abs().mean()
+        loss.backward()
+        return float(loss.detach().cpu()), gg.grad.cpu()
+
+    for _ in range(3):
+        step_e2e()
+    barrier()
+    e0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e()
+    barrier()
+    e_wall = time.perf_counter() - e0
+    t = torch.tensor([e_wall], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * V * args.steps / float(t.item())
+
+    if rank == 0:
+        hbm, peak_src = measured_peaks()
+        HW = H * W
+        # algorithmic bytes per launch (DESIGN.md "Kernels"): one launch covers all NV views
+        bytes_k3 = 76.0 * D + 40.0 * HW * V
+        bytes_k4 = 76.0 * D + 60.0 * HW * V + 72.0 * P * V
+        names = ["preprocess", "binning", "render_fwd", "render_bwd", "preprocess_bwd"]
+        stages = {n: float(stage_ms[i]) for i, n in enumerate(names)}
+        if stages["render_bwd"] >= stages["render_fwd"]:
+            dom, dom_bytes = "render_bwd", bytes_k4
+        else:
+            dom, dom_bytes = "render_fwd", bytes_k3
+        achieved = dom_bytes / (stages[dom] * 1e-3) / 1e9
+        step_bytes = V * (52.0 * P + 40.0 * HW) + 76.0 * D + V * (60.0 * HW + 104.0 * P) + 76.0 * D
+        cpu_v, cpu_n, cpu_dt = cpu_views_per_s(2, 10.0)
+        out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+               "warmup": max(args.warmup, 3), "ms_per_step": dev_ms_max / args.steps,
+               "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+               "data": "synthetic", "config": dict(CONFIG, instances_D=D),
+               "wall_s_timed_region": wall, "stage_ms": stages,
+               "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": hbm, "unit": "GB/s",
+                            "frac": achieved / hbm, "traffic": None, "peak_source": peak_src,
+                            "algorithmic_bytes_per_launch": dom_bytes,
+                            "whole_step_algorithmic_GBs": step_bytes / (dev_ms_max / args.steps * 1e-3) / 1e9},
+               "cpu_baseline": {"value": cpu_v, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                                "sample": "%d views fwd+bwd of the same 100k/512^2 scene in %.1f s "
+                                          "(oracle/surfel_oracle.c, OpenMP)" % (cpu_n, cpu_dt)},
+               "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+               "gpu_launches": 7 * args.steps, "clocks": clocks}
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,154 @@
+// K2: tile binning and per-tile depth sort.
+//
+// Upstream (rasterizer_impl.cu) builds one global list of 64-bit keys
+// (tile<<32 | depth bits), runs a device-wide radix sort and reads the
+// instance count back to the host.  Here: K1 has already counted instances
+// per tile; (a) one block scans the per-tile counts into tile ranges,
+// (b) every surfel scatters (depth bits<<32 | surfel) into its tiles' ranges,
+// (c) one block per tile sorts its range in shared memory.  Because the keys
+// are unique, the sorted order equals upstream's stable sort of the
+// duplication order (ascending surfel index) -- bit-exact -- without a global
+// sort, without a host read-back and with ~3 passes over 8-byte keys instead
+// of ~10 over 12-byte pairs.
+#include "raster_common.cuh"
+
+#define SCAN_THREADS 1024
+
+__global__ void __launch_bounds__(SCAN_THREADS)
+scan_tiles_kernel(RasterDims d, RasterWs ws)
+{
+    __shared__ uint32_t s_warp[32];
+    __shared__ uint32_t s_carry;
+    const int n = d.NV * d.T;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int base = 0; base < n; base += SCAN_THREADS) {
+        const int i = base + threadIdx.x;
+        uint32_t v = (i < n) ? ws.tile_count[i] : 0u;
+        uint32_t x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o) x += y;
+        }
+        if (lane == 31) s_warp[warp] = x;
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t wv = s_warp[lane], wx = wv;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                uint32_t y = __shfl_up_sync(0xffffffffu, wx, o);
+                if (lane >= o) wx += y;
+            }
+            s_warp[lane] = wx - wv;   // exclusive warp offsets
+        }
+        __syncthreads();
+        const uint32_t carry = s_carry;
+        const uint32_t excl = carry + s_warp[warp] + x - v;
+        if (i < n) {
+            ws.tile_start[i] = excl;
+            ws.tile_count[i] = 0;       // becomes the scatter fill cursor
+        }
+        __syncthreads();
+        if (threadIdx.x == SCAN_THREADS - 1) s_carry = excl + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const uint32_t total = s_carry;
+        ws.tile_start[n] = total;
+        ws.status[0] = (int32_t)total;
+        ws.status[1] = ((int64_t)total > d.max_instances) ? 1 : 0;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+scatter_kernel(RasterDims d, RasterWs ws)
+{
+    const int view = blockIdx.y;
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= d.P || ws.status[1]) return;
+    const size_t vi = (size_t)view * d.P + i;
+    const uint32_t r = ws.rect[vi];
+    if (r == 0) return;
+    const int x0 = r & 255, y0 = (r >> 8) & 255, x1 = (r >> 16) & 255, y1 = r >> 24;
+    const unsigned long long key =
+        ((unsigned long long)__float_as_uint(ws.depth[vi]) << 32) | (unsigned long long)(uint32_t)i;
+    for (int y = y0; y < y1; y++)
+        for (int x = x0; x < x1; x++) {
+            const size_t t = (size_t)view * d.T + y * d.gx + x;
+            const uint32_t slot = atomicAdd(&ws.tile_count[t], 1u);
+            ws.keys[ws.tile_start[t] + slot] = key;
+        }
+}
+
+// Ascending-only bitonic network (flip + half-cleaners): every compare-exchange
+// moves the minimum to the lower index, so virtual +inf padding beyond n never
+// moves and n need not be a power of two.  Works on shared or global memory.
+__device__ __forceinline__ void block_bitonic_sort(unsigned long long *a, int n)
+{
+    int n2 = 1;
+    while (n2 < n) n2 <<= 1;
+    for (int k = 2; k <= n2; k <<= 1) {
+        // flip step: partner = mirror inside the k-block
+        for (int t = threadIdx.x; t < n2 / 2; t += blockDim.x) {
+            const int blk = t / (k / 2), off = t % (k / 2);
+            const int i = blk * k + off, p = blk * k + k - 1 - off;
+            if (p < n) {
+                unsigned long long x = a[i], y = a[p];
+                if (x > y) { a[i] = y; a[p] = x; }
+            }
+        }
+        __syncthreads();
+        for (int j = k / 4; j >= 1; j >>= 1) {
+            for (int t = threadIdx.x; t < n2 / 2; t += blockDim.x) {
+                const int i = (t / j) * 2 * j + (t % j), p = i + j;
+                if (p < n) {
+                    unsigned long long x = a[i], y = a[p];
+                    if (x > y) { a[i] = y; a[p] = x; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+#define SORT_SMEM_KEYS 4096
+
+__global__ void __launch_bounds__(256)
+sort_tiles_kernel(RasterDims d, RasterWs ws)
+{
+    __shared__ unsigned long long s_keys[SORT_SMEM_KEYS];
+    if (ws.status[1]) return;
+    const size_t t = blockIdx.x;
+    const uint32_t start = ws.tile_start[t], end = ws.tile_start[t + 1];
+    const int n = (int)(end - start);
+    if (n == 0) return;
+    unsigned long long *gk = ws.keys + start;
+    if (n <= SORT_SMEM_KEYS) {
+        for (int i = threadIdx.x; i < n; i += blockDim.x) s_keys[i] = gk[i];
+        __syncthreads();
+        if (n > 1) block_bitonic_sort(s_keys, n);
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            const unsigned long long k = s_keys[i];
+            gk[i] = k;
+            ws.ids[start + i] = (uint32_t)(k & 0xffffffffull);
+        }
+    } else {
+        // rare: a tile with more instances than fit in shared memory is sorted
+        // in place in global memory (L2 resident) by the same network.
+        if (threadIdx.x == 0) atomicAdd(&ws.status[2], 1);
+        block_bitonic_sort(gk, n);
+        for (int i = threadIdx.x; i < n; i += blockDim.x)
+            ws.ids[start + i] = (uint32_t)(gk[i] & 0xffffffffull);
+    }
+}
+
+cudaError_t ga_launch_binning(const RasterDims &d, const RasterWs &w, cudaStream_t s)
+{
+    scan_tiles_kernel<<<1, SCAN_THREADS, 0, s>>>(d, w);
+    dim3 grid((d.P + 255) / 256, d.NV);
+    scatter_kernel<<<grid, 256, 0, s>>>(d, w);
+    sort_tiles_kernel<<<d.NV * d.T, 256, 0, s>>>(d, w);
+    return cudaGetLastError();
+}

@@ -1,0 +1,57 @@
+// Shared definitions of the surfel rasteriser kernels (sm_100a).
+// Algorithm: github.com/hbb1/diff-surfel-rasterization as called by
+// /root/reference/nsr/gs_surfel.py:85-114; constants per SURVEY.md App. A.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define GA_BLOCK_X 16
+#define GA_BLOCK_Y 16
+#define GA_NEAR_N 0.2f
+#define GA_FAR_N 100.0f
+#define GA_FILTER_SIZE 0.707106f
+#define GA_FILTER_INV_SQUARE 2.0f
+#define GA_CUTOFF 3.0f
+#define GA_REC_F 24
+#define GA_GRAD_F 18
+
+// record float offsets (6 x float4):
+//  q0 = Tu.x Tu.y Tu.z Tv.x | q1 = Tv.y Tv.z Tw.x Tw.y | q2 = Tw.z xy.x xy.y opacity
+//  q3 = n.x n.y n.z r        | q4 = bbox x0 x1 y0 y1    | q5 = g b - -
+// gradient accumulator float offsets:
+//  0-8 dL/dT (Tu,Tv,Tw) | 9-10 dL/dmean2D | 11-13 dL/dnormal | 14 dL/dopacity | 15-17 dL/drgb
+
+struct RasterDims {
+    int batch, P, views, NV;   // NV = batch*views images
+    int H, W, gx, gy, T;       // T = gx*gy tiles per image
+    float scale_modifier;
+    int64_t max_instances;
+};
+
+struct RasterWs {
+    int32_t *status;
+    float *rec;
+    float *depth;
+    uint32_t *rect;
+    uint32_t *tile_count;
+    uint32_t *tile_start;
+    unsigned long long *keys;
+    uint32_t *ids;
+    float *final_T;
+    int32_t *n_contrib;
+};
+
+// kernel launchers (defined in the .cu files, called from raster_api.cu)
+cudaError_t ga_launch_preprocess(const RasterDims &d, const RasterWs &w, const float *gauss13,
+                                 const float *viewmats, const float *projmats,
+                                 int32_t *out_radii, cudaStream_t s);
+cudaError_t ga_launch_binning(const RasterDims &d, const RasterWs &w, cudaStream_t s);
+cudaError_t ga_launch_render_fwd(const RasterDims &d, const RasterWs &w, const float *bg,
+                                 float *out_color, float *out_allmap, cudaStream_t s);
+cudaError_t ga_launch_render_bwd(const RasterDims &d, const RasterWs &w, const float *bg,
+                                 const float *dL_dcolor, const float *dL_dallmap,
+                                 float *grad_acc, cudaStream_t s);
+cudaError_t ga_launch_preprocess_bwd(const RasterDims &d, const RasterWs &w, const float *gauss13,
+                                     const float *viewmats, const float *projmats,
+                                     const int32_t *radii, const float *grad_acc,
+                                     float *grad_gauss13, cudaStream_t s);

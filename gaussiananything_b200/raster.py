@@ -1,0 +1,126 @@
+"""Batched surfel rasterisation: torch plumbing over the C ABI.
+
+One call renders every (batch item, view) pair -- the whole double loop of
+/root/reference/nsr/gs_surfel.py:65-176 -- with one launch set.  Tensors are
+only used for device memory, the current stream and autograd bookkeeping; all
+arithmetic happens in libga_b200.so.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+
+_capacity_hint = {}
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr())
+
+
+def _stream(dev):
+    return C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+def layout(batch, P, views, H, W, max_instances):
+    L = _lib.GaRasterLayout()
+    _lib.check(_lib.lib().ga_raster_layout(batch, P, views, H, W, max_instances, C.byref(L)),
+               "ga_raster_layout")
+    return L
+
+
+def workspace_views(ws, L, batch, P, views, H, W, max_instances):
+    """Typed views of the workspace sections (for tests / debugging)."""
+    NV, T, HW = batch * views, ((W + 15) // 16) * ((H + 15) // 16), H * W
+
+    def sec(off, dtype, n):
+        esz = torch.empty(0, dtype=dtype).element_size()
+        return ws[off:off + n * esz].view(dtype)
+    return dict(
+        status=sec(L.status, torch.int32, 16),
+        rec=sec(L.rec, torch.float32, NV * P * 24).view(NV, P, 24),
+        depth=sec(L.depth, torch.float32, NV * P).view(NV, P),
+        rect=sec(L.rect, torch.int32, NV * P).view(NV, P),
+        tile_start=sec(L.tile_start, torch.int32, NV * T + 1),
+        keys=sec(L.keys, torch.int64, max_instances),
+        ids=sec(L.ids, torch.int32, max_instances),
+        final_T=sec(L.final_T, torch.float32, NV * 3 * HW).view(NV, 3, H, W),
+        n_contrib=sec(L.n_contrib, torch.int32, NV * 2 * HW).view(NV, 2, H, W),
+    )
+
+
+def forward_raw(gauss13, viewmats, projmats, bg, H, W, scale_modifier=1.0, max_instances=None):
+    """gauss13 [B,P,13], viewmats/projmats [B,V,4,4] (reference layout), bg [3].
+    Returns (color [B,V,3,H,W], allmap [B,V,7,H,W], radii [B,V,P], state)."""
+    lib = _lib.lib()
+    if not gauss13.is_cuda:
+        raise RuntimeError("gaussiananything_b200 rasteriser needs CUDA tensors (no CPU fallback)")
+    dev = gauss13.device
+    B, P, c = gauss13.shape
+    assert c == 13
+    V = viewmats.shape[1]
+    gauss13 = gauss13.contiguous().float()
+    viewmats = viewmats.reshape(B * V, 16).contiguous().float()
+    projmats = projmats.reshape(B * V, 16).contiguous().float()
+    bg = bg.to(device=dev, dtype=torch.float32).contiguous()
+    key = (B, P, V, H, W)
+    if max_instances is None:
+        max_instances = _capacity_hint.get(key, 4 * B * V * P + 1024)
+    color = torch.empty(B, V, 3, H, W, device=dev, dtype=torch.float32)
+    allmap = torch.empty(B, V, 7, H, W, device=dev, dtype=torch.float32)
+    radii = torch.empty(B, V, P, device=dev, dtype=torch.int32)
+    while True:
+        L = layout(B, P, V, H, W, max_instances)
+        ws = torch.empty(L.total_bytes, device=dev, dtype=torch.uint8)
+        rc = lib.ga_raster_forward(_ptr(gauss13), B, P, V, _ptr(viewmats), _ptr(projmats), _ptr(bg),
+                                   H, W, float(scale_modifier), _ptr(color), _ptr(allmap), _ptr(radii),
+                                   _ptr(ws), L.total_bytes, max_instances, _stream(dev))
+        _lib.check(rc, "ga_raster_forward")
+        status = ws[L.status:L.status + 64].view(torch.int32).cpu()   # one sync per call
+        if int(status[1]) == 0:
+            break
+        max_instances = int(int(status[0]) * 1.25) + 1024
+        _capacity_hint[key] = max_instances
+    state = dict(ws=ws, L=L, max_instances=max_instances, num_rendered=int(status[0]),
+                 gauss13=gauss13, viewmats=viewmats, projmats=projmats, bg=bg,
+                 dims=(B, P, V, H, W), scale_modifier=float(scale_modifier), radii=radii)
+    return color, allmap, radii, state
+
+
+def backward_raw(state, grad_color, grad_allmap):
+    lib = _lib.lib()
+    B, P, V, H, W = state["dims"]
+    dev = state["gauss13"].device
+    grad_color = grad_color.contiguous().float()
+    grad_allmap = grad_allmap.contiguous().float()
+    nbytes = lib.ga_raster_backward_scratch_bytes(B, P, V)
+    scratch = torch.empty(nbytes, device=dev, dtype=torch.uint8)
+    grad = torch.empty(B, P, 13, device=dev, dtype=torch.float32)
+    rc = lib.ga_raster_backward(_ptr(state["gauss13"]), B, P, V, _ptr(state["viewmats"]),
+                                _ptr(state["projmats"]), _ptr(state["bg"]), H, W,
+                                state["scale_modifier"], _ptr(state["radii"]),
+                                _ptr(grad_color), _ptr(grad_allmap),
+                                _ptr(state["ws"]), state["L"].total_bytes, state["max_instances"],
+                                _ptr(scratch), nbytes, _ptr(grad), _stream(dev))
+    _lib.check(rc, "ga_raster_backward")
+    return grad
+
+
+class _RasterizeSurfelsBatched(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, gauss13, viewmats, projmats, bg, H, W, scale_modifier):
+        color, allmap, radii, state = forward_raw(gauss13, viewmats, projmats, bg, H, W, scale_modifier)
+        ctx.state = state
+        ctx.mark_non_differentiable(radii)
+        return color, allmap, radii
+
+    @staticmethod
+    def backward(ctx, grad_color, grad_allmap, _grad_radii):
+        grad = backward_raw(ctx.state, grad_color, grad_allmap)
+        return grad, None, None, None, None, None, None
+
+
+def rasterize_surfels_batched(gauss13, viewmats, projmats, bg, H, W, scale_modifier=1.0):
+    """Differentiable batched rasterisation (grad w.r.t. gauss13 only, like the
+    reference, whose cameras and background carry no gradient)."""
+    return _RasterizeSurfelsBatched.apply(gauss13, viewmats, projmats, bg, H, W, scale_modifier)

@@ -1,0 +1,268 @@
+"""GPU parity tests of the surfel rasteriser: CUDA path (through the C ABI)
+against the CPU oracle on identical seeded inputs.
+
+Bars (SURVEY.md 8d / BASELINE.json north_star): integer tile/bin indices
+bit-exact; rendered RGB-D(+alpha, normal, distortion) rel-L2 <= 1e-3;
+gradients rel-L2 <= 1e-3.  The oracle itself is PARITY UNPINNED (upstream
+rasteriser not vendored, no reference tests) -- see oracle/surfel_oracle.c.
+"""
+import numpy as np
+import pytest
+import torch
+
+from tests.helpers import cameras, oracle_view, rel_l2, scene
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-3
+
+
+def _run_cuda(g, views, projs, bg, H, W, scale_modifier=1.0, batch=1):
+    from gaussiananything_b200 import raster
+    dev = torch.device("cuda:0")
+    P = g.shape[-2]
+    g13 = torch.tensor(g, device=dev).reshape(batch, P, 13)
+    V = views.shape[0] // batch
+    vm = torch.tensor(views, device=dev).reshape(batch, V, 4, 4)
+    pm = torch.tensor(projs, device=dev).reshape(batch, V, 4, 4)
+    bgt = torch.tensor(bg, dtype=torch.float32, device=dev)
+    color, allmap, radii, state = raster.forward_raw(g13, vm, pm, bgt, H, W, scale_modifier)
+    wsv = raster.workspace_views(state["ws"], state["L"], batch, P, V, H, W, state["max_instances"])
+    return color, allmap, radii, state, wsv
+
+
+def _check_view(o, color, allmap, radii, wsv, nv, P, H, W, tol=TOL):
+    T = ((W + 15) // 16) * ((H + 15) // 16)
+    # --- integers: bit exact
+    assert np.array_equal(radii.cpu().numpy(), o["radii"]), "radii differ"
+    rect = wsv["rect"][nv].cpu().numpy().astype(np.uint32)
+    orect = o["rect"].astype(np.uint32)
+    packed = orect[:, 0] | (orect[:, 1] << 8) | (orect[:, 2] << 16) | (orect[:, 3] << 24)
+    assert np.array_equal(rect, packed), "tile rects differ"
+    assert np.array_equal(wsv["depth"][nv].cpu().numpy().view(np.uint32), o["depth"].view(np.uint32)), "depth bits differ"
+    ts = wsv["tile_start"].cpu().numpy()[nv * T:(nv + 1) * T + 1].astype(np.int64)
+    base = ts[0]
+    rng = o["ranges"].astype(np.int64)
+    cnt = rng[:, 1] - rng[:, 0]
+    assert np.array_equal(ts[1:] - ts[:-1], cnt), "tile ranges differ"
+    D = o["num_rendered"]
+    ids = wsv["ids"].cpu().numpy()[base:base + D].astype(np.uint32)
+    assert np.array_equal(ids, o["ids"]), "sorted surfel ids differ"
+    keys = wsv["keys"].cpu().numpy()[base:base + D].view(np.uint64)
+    assert np.array_equal((keys >> np.uint64(32)).astype(np.uint32), (o["keys"] & np.uint64(0xffffffff)).astype(np.uint32)), "depth keys differ"
+    # --- floats
+    c = color.cpu().numpy(); a = allmap.cpu().numpy()
+    assert rel_l2(c, o["color"]) <= tol, ("color", rel_l2(c, o["color"]))
+    for ch, name in enumerate(["depth", "alpha", "nx", "ny", "nz", "median_depth", "distortion"]):
+        if np.linalg.norm(o["allmap"][ch]) == 0:
+            assert np.abs(a[ch]).max() <= 1e-6
+            continue
+        r = rel_l2(a[ch], o["allmap"][ch])
+        if name == "median_depth":
+            # a pixel whose T crosses 0.5 within rounding picks a different surfel: bound the count
+            bad = np.abs(a[ch] - o["allmap"][ch]) > 1e-4 * np.maximum(1.0, np.abs(o["allmap"][ch]))
+            assert bad.mean() <= 2e-4, (name, bad.mean())
+        else:
+            assert r <= tol, (name, r)
+    nc = wsv["n_contrib"][nv].cpu().numpy()
+    mism = (nc[0] != o["n_contrib"][0]).mean()
+    assert mism <= 2e-4, ("n_contrib mismatch rate", mism)
+
+
+@pytest.mark.parametrize("P,H,W,boost,seed", [
+    (10000, 256, 256, 1.0, 0),      # BASELINE config C1 shape
+    (3000, 250, 300, 8.0, 1),       # ragged image, larger splats
+    (500, 64, 48, 40.0, 2),         # big splats: many tiles each, early termination
+    (1, 32, 32, 40.0, 3),           # single surfel
+    (4000, 128, 128, 1.0, 4),
+])
+def test_forward_parity_single_view(P, H, W, boost, seed):
+    g = scene(P, seed, boost)
+    vs, ps, _, _ = cameras(1, start=seed)
+    bg = [1.0, 0.5, 0.2]
+    color, allmap, radii, state, wsv = _run_cuda(g, vs, ps, bg, H, W)
+    o = oracle_view(g, vs[0], ps[0], bg, H, W)
+    assert state["num_rendered"] == o["num_rendered"]
+    _check_view(o, color[0, 0], allmap[0, 0], radii[0, 0], wsv, 0, P, H, W)
+
+
+def test_forward_parity_batched_views_and_batches():
+    B, V, P, H, W = 2, 3, 2500, 160, 144
+    g = np.stack([scene(P, 10, 6.0), scene(P, 11, 3.0)])
+    vs, ps, _, _ = cameras(B * V)
+    bg = [1.0, 1.0, 1.0]
+    color, allmap, radii, state, wsv = _run_cuda(g, vs, ps, bg, H, W, batch=B)
+    tot = 0
+    for b in range(B):
+        for v in range(V):
+            nv = b * V + v
+            o = oracle_view(g[b], vs[nv], ps[nv], bg, H, W)
+            tot += o["num_rendered"]
+            _check_view(o, color[b, v], allmap[b, v], radii[b, v], wsv, nv, P, H, W)
+    assert tot == state["num_rendered"]
+
+
+def test_all_culled_and_empty_tiles():
+    P, H, W = 256, 64, 64
+    g = scene(P, 5)
+    g[:, 0:3] += 100.0          # far outside the frustum / behind the camera for some views
+    vs, ps, _, _ = cameras(1)
+    bg = [0.25, 0.5, 0.75]
+    color, allmap, radii, state, wsv = _run_cuda(g, vs, ps, bg, H, W)
+    o = oracle_view(g, vs[0], ps[0], bg, H, W)
+    assert state["num_rendered"] == o["num_rendered"]
+    assert np.array_equal(radii[0, 0].cpu().numpy(), o["radii"])
+    assert rel_l2(color[0, 0].cpu().numpy(), o["color"]) <= 1e-6
+
+
+def test_scale_modifier_and_low_opacity():
+    P, H, W = 2000, 96, 96
+    g = scene(P, 6, 10.0)
+    g[::3, 3] = 0.001           # below 1/255: stays in the lists, never contributes
+    vs, ps, _, _ = cameras(1)
+    bg = [0.0, 0.0, 0.0]
+    color, allmap, radii, state, wsv = _run_cuda(g, vs, ps, bg, H, W, scale_modifier=1.7)
+    o = oracle_view(g, vs[0], ps[0], bg, H, W, scale_modifier=1.7)
+    _check_view(o, color[0, 0], allmap[0, 0], radii[0, 0], wsv, 0, P, H, W)
+
+
+def test_sort_fallback_large_tile():
+    # > 4096 instances in one tile -> the global-memory sort path
+    P, H, W = 6000, 32, 32
+    g = scene(P, 7, 1.0)
+    g[:, 0:3] *= 0.02
+    vs, ps, _, _ = cameras(1)
+    bg = [1.0, 1.0, 1.0]
+    color, allmap, radii, state, wsv = _run_cuda(g, vs, ps, bg, H, W)
+    o = oracle_view(g, vs[0], ps[0], bg, H, W)
+    assert int(wsv["status"][2]) >= 1, "expected at least one tile on the fallback sort"
+    _check_view(o, color[0, 0], allmap[0, 0], radii[0, 0], wsv, 0, P, H, W)
+
+
+def test_workspace_overflow_retry():
+    from gaussiananything_b200 import raster
+    P, H, W = 3000, 128, 128
+    g = scene(P, 8, 20.0)
+    vs, ps, _, _ = cameras(1)
+    dev = torch.device("cuda:0")
+    g13 = torch.tensor(g, device=dev)[None]
+    vm = torch.tensor(vs, device=dev)[None]
+    pm = torch.tensor(ps, device=dev)[None]
+    bg = torch.ones(3, device=dev)
+    c1, a1, r1, s1 = raster.forward_raw(g13, vm, pm, bg, H, W, max_instances=16)   # forces a retry
+    o = oracle_view(g, vs[0], ps[0], [1, 1, 1], H, W)
+    assert s1["num_rendered"] == o["num_rendered"]
+    assert rel_l2(c1[0, 0].cpu().numpy(), o["color"]) <= TOL
+
+
+@pytest.mark.parametrize("P,H,W,boost,seed,V", [
+    (2000, 96, 112, 10.0, 20, 1),
+    (800, 64, 64, 40.0, 21, 2),
+    (10000, 256, 256, 1.0, 22, 1),
+])
+def test_backward_parity(P, H, W, boost, seed, V):
+    from gaussiananything_b200 import raster
+    from oracle import surfel_oracle as so
+    g = scene(P, seed, boost)
+    vs, ps, _, _ = cameras(V, start=seed)
+    bg = [1.0, 0.5, 0.2]
+    dev = torch.device("cuda:0")
+    g13 = torch.tensor(g, device=dev)[None].requires_grad_(True)
+    vm = torch.tensor(vs, device=dev)[None]
+    pm = torch.tensor(ps, device=dev)[None]
+    color, allmap, radii = raster.rasterize_surfels_batched(g13, vm, pm, torch.tensor(bg, device=dev), H, W, 1.0)
+    rng = np.random.default_rng(seed)
+    gc = rng.standard_normal((V, 3, H, W)).astype(np.float32)
+    ga = rng.standard_normal((V, 7, H, W)).astype(np.float32)
+    loss = (color[0] * torch.tensor(gc, device=dev)).sum() + (allmap[0] * torch.tensor(ga, device=dev)).sum()
+    loss.backward()
+    got = g13.grad[0].cpu().numpy().astype(np.float64)
+    want = np.zeros((P, 13))
+    for v in range(V):
+        o = oracle_view(g, vs[v], ps[v], bg, H, W)
+        b = so.rasterize_backward(o, gc[v], ga[v])
+        want[:, 0:3] += b["means3D"]; want[:, 3:4] += b["opacities"]; want[:, 4:6] += b["scales"]
+        want[:, 6:10] += b["rotations"]; want[:, 10:13] += b["colors"]
+    for name, sl in [("means3D", slice(0, 3)), ("opacity", slice(3, 4)), ("scales", slice(4, 6)),
+                     ("rotations", slice(6, 10)), ("colors", slice(10, 13))]:
+        r = rel_l2(got[:, sl], want[:, sl])
+        assert r <= TOL, (name, r)
+
+
+def test_reference_api_surface():
+    """diff_surfel_rasterization / GaussianRenderer2DGS mirrors give the same pixels as the batched call."""
+    from gaussiananything_b200.diff_surfel_rasterization import GaussianRasterizationSettings, GaussianRasterizer
+    from gaussiananything_b200.gs_surfel import GaussianRenderer2DGS
+    P, H = 3000, 128
+    g = scene(P, 30, 5.0)
+    vs, ps, cs, tf = cameras(2)
+    dev = torch.device("cuda:0")
+    gt = torch.tensor(g, device=dev)
+    bg = torch.tensor([1.0, 1.0, 1.0], device=dev)
+    rs = GaussianRasterizationSettings(image_height=H, image_width=H, tanfovx=tf, tanfovy=tf, bg=bg,
+                                       scale_modifier=1.0, viewmatrix=torch.tensor(vs[0], device=dev),
+                                       projmatrix=torch.tensor(ps[0], device=dev), sh_degree=0,
+                                       campos=torch.tensor(cs[0], device=dev), prefiltered=False, debug=False)
+    rast = GaussianRasterizer(raster_settings=rs)
+    img, radii, allmap = rast(means3D=gt[:, 0:3], means2D=torch.zeros_like(gt[:, 0:3]), shs=None,
+                              colors_precomp=gt[:, 10:13], opacities=gt[:, 3:4], scales=gt[:, 4:6],
+                              rotations=gt[:, 6:10], cov3D_precomp=None)
+    assert img.shape == (3, H, H) and allmap.shape == (7, H, H) and radii.shape == (P,)
+    assert radii.dtype == torch.int32
+    o = oracle_view(g, vs[0], ps[0], [1, 1, 1], H, H)
+    assert rel_l2(img.cpu().numpy(), o["color"]) <= TOL
+    with pytest.raises(Exception):
+        rast(means3D=gt[:, 0:3], means2D=None, opacities=gt[:, 3:4], shs=None, colors_precomp=None,
+             scales=gt[:, 4:6], rotations=gt[:, 6:10])
+    r = GaussianRenderer2DGS(H, 3, {})
+    out = r.render(gt[None], torch.tensor(vs, device=dev)[None], torch.tensor(ps, device=dev)[None],
+                   torch.tensor(cs, device=dev)[None], tf)
+    assert out["image"].shape == (1, 2, 3, H, H) and out["rend_normal"].shape == (1, 2, 3, H, H)
+    assert out["alpha"].shape == (1, 2, 1, H, H) and out["depth"].shape == (1, 2, 1, H, H)
+    assert rel_l2(out["image"][0, 0].cpu().numpy(), np.clip(o["color"], 0, 1)) <= TOL
+    # normals rotated camera->world exactly like the reference post-processing (gs_surfel.py:125-128)
+    n_ref = np.einsum('chw,dc->dhw', o["allmap"][2:5], vs[0][:3, :3])
+    assert rel_l2(out["rend_normal"][0, 0].cpu().numpy(), n_ref) <= TOL
+
+
+def test_full_size_properties():
+    """BASELINE config C2 size (100k surfels, 512^2, 6 views): size-independent properties."""
+    from gaussiananything_b200 import raster
+    P, H, W, V = 100000, 512, 512, 6
+    g = scene(P, 40)
+    vs, ps, _, _ = cameras(V)
+    dev = torch.device("cuda:0")
+    g13 = torch.tensor(g, device=dev)[None]
+    vm = torch.tensor(vs, device=dev)[None]
+    pm = torch.tensor(ps, device=dev)[None]
+    bg = torch.ones(3, device=dev)
+    c1, a1, r1, s1 = raster.forward_raw(g13, vm, pm, bg, H, W)
+    # 1. batched == per-view calls, bit for bit (views are independent)
+    for v in (0, 5):
+        c2, a2, r2, s2 = raster.forward_raw(g13, vm[:, v:v + 1], pm[:, v:v + 1], bg, H, W)
+        assert torch.equal(c1[:, v], c2[:, 0]) and torch.equal(a1[:, v], a2[:, 0]) and torch.equal(r1[:, v], r2[:, 0])
+    # 2. deterministic forward
+    c3, a3, r3, s3 = raster.forward_raw(g13, vm, pm, bg, H, W)
+    assert torch.equal(c1, c3) and torch.equal(a1, a3)
+    # 3. ranges: alpha in [0,1), colour = C + T*bg with bg=1 -> within [0, 1+eps]
+    assert float(a1[:, :, 1].min()) >= 0.0 and float(a1[:, :, 1].max()) < 1.0
+    assert float(c1.min()) >= -1e-5 and float(c1.max()) <= 1.0 + 1e-4
+    # 4. every tile list is depth sorted and sum(tile counts) == D
+    wsv = raster.workspace_views(s1["ws"], s1["L"], 1, P, V, H, W, s1["max_instances"])
+    D = s1["num_rendered"]
+    ts = wsv["tile_start"].cpu().numpy().astype(np.int64)
+    assert ts[-1] == D
+    keys = wsv["keys"][:D].cpu().numpy().view(np.uint64)
+    seg = np.zeros(D, dtype=bool); seg[ts[:-1][ts[:-1] < D]] = True
+    inc = keys[1:] > keys[:-1]
+    assert np.all(inc | seg[1:]), "a tile list is not strictly sorted"
+    # 5. one view against the oracle at full size
+    o = oracle_view(g, vs[2], ps[2], [1, 1, 1], H, W)
+    assert rel_l2(c1[0, 2].cpu().numpy(), o["color"]) <= TOL
+    assert np.array_equal(r1[0, 2].cpu().numpy(), o["radii"])
+    # 6. backward is linear in the upstream gradient
+    torch.manual_seed(0)
+    g1 = torch.randn_like(c1); g2 = torch.randn_like(a1)
+    ga = raster.backward_raw(s1, g1, g2)
+    gb = raster.backward_raw(s1, 2.0 * g1, 2.0 * g2)
+    assert rel_l2(gb.cpu().numpy(), 2.0 * ga.cpu().numpy()) <= 1e-4
