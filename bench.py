@@ -54,7 +54,7 @@ def make_inputs(seed):
 
 class ClockSampler:
     """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+    Q = ("timestamp,clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
@@ -65,7 +65,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                 "--format=csv,noheader,nounits", "-lms", "100"],
+                 "--format=csv,noheader,nounits", "-lms", "20"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -76,21 +76,32 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append([x.strip() for x in line.split(",")])
 
+    def mark(self):
+        """Rows sampled from now on belong to the timed region."""
+        self.mark_idx = len(self.rows)
+
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.05)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        rows = [r for r in self.rows if len(r) >= 7]
+        timed = rows[getattr(self, "mark_idx", 0):]
+        window = "timed region"
+        if len(timed) < 3:      # region shorter than the sampling period: include the warm-up (same workload)
+            timed, window = rows, "warm-up + timed region (timed region shorter than 3 samples)"
+        sm = [float(r[1]) for r in timed if r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in timed if r[2].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = [n for k, n in enumerate(names)
-                   if any(len(r) >= 6 and r[2 + k].lower().startswith("active") for r in self.rows)]
+                   if any(r[3 + k].lower().startswith("active") for r in timed)]
         return {"sm_mhz": float(np.median(sm)) if sm else None,
-                "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
+                "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm),
+                "window": window}
 
 
 # ---------------------------------------------------------------------------
@@ -203,14 +214,17 @@ def run_gpu(args):
         torch.cuda.synchronize(dev)
 
     # ---- device-resident throughput ("value") + per-stage timing (roofline)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)                              # let nvidia-smi start sampling
     for _ in range(max(args.warmup, 3)):
         flush.zero_()
         step_device()
     torch.cuda.synchronize(dev)
     lib.ga_profile_enable(1)
-    sampler = ClockSampler(local)
     if rank == 0:
-        sampler.start()
+        sampler.mark()
     stage_ms = np.zeros(8)
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
@@ -309,7 +323,7 @@ def run_gpu(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     args = ap.parse_args()

@@ -50,22 +50,33 @@ __device__ __forceinline__ bool eval_pair(const float4 a, const float4 b, const 
     return o.alpha >= 1.0f / 255.0f;
 }
 
+// Forward staging record (tile-local, computed once per (tile, surfel) by the
+// staging thread): with o = tile origin, k_o = o.x*Tw - Tu, l_o = o.y*Tw - Tv,
+//   p(dx,dy) = (k_o + dx*Tw) x (l_o + dy*Tw) = C + dx*A + dy*B,
+//   C = k_o x l_o, A = Tw x l_o, B = k_o x Tw            (Tw x Tw = 0)
+// which is upstream's cross(k, l) re-associated around the tile origin (all
+// terms stay O(tile size), so no precision is lost) and costs 6 FMAs per pixel.
+//  f0 = C.x C.y C.z A.x | f1 = A.y A.z B.x B.y | f2 = B.z Tw.x Tw.y Tw.z
+//  f3 = xy.x-o.x xy.y-o.y opacity - | f4 = cull box (tile-local x0 x1 y0 y1)
+//  f5 = n.x n.y n.z r | f6 = g b - -
 __global__ void __launch_bounds__(256)
 render_fwd_kernel(RasterDims d, RasterWs ws, const float *__restrict__ bg,
                   float *__restrict__ out_color, float *__restrict__ out_allmap)
 {
-    __shared__ float4 s_rec[6][CHUNK];
+    __shared__ float4 s_rec[7][CHUNK];
     if (ws.status[1]) return;
     const int view = blockIdx.z;
     const int tile = blockIdx.y * d.gx + blockIdx.x;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int wx0 = blockIdx.x * GA_BLOCK_X + (warp & 1) * 8;
-    const int wy0 = blockIdx.y * GA_BLOCK_Y + (warp >> 1) * 4;
-    const int pxi = wx0 + (lane & 7), pyi = wy0 + (lane >> 3);
+    const int ox = blockIdx.x * GA_BLOCK_X, oy = blockIdx.y * GA_BLOCK_Y;
+    const int lx0 = (warp & 1) * 8, ly0 = (warp >> 1) * 4;       // warp's 8x4 block, tile-local
+    const int lxi = lx0 + (lane & 7), lyi = ly0 + (lane >> 3);
+    const int pxi = ox + lxi, pyi = oy + lyi;
     const bool inside = pxi < d.W && pyi < d.H;
-    const float pfx = (float)pxi, pfy = (float)pyi;
-    const float bx_lo = (float)wx0, bx_hi = (float)(wx0 + 7);
-    const float by_lo = (float)wy0, by_hi = (float)(wy0 + 3);
+    const float dxf = (float)lxi, dyf = (float)lyi;
+    const float bx_lo = (float)lx0, bx_hi = (float)(lx0 + 7);
+    const float by_lo = (float)ly0, by_hi = (float)(ly0 + 3);
+    const float oxf = (float)ox, oyf = (float)oy;
 
     const uint32_t start = ws.tile_start[(size_t)view * d.T + tile];
     const uint32_t end = ws.tile_start[(size_t)view * d.T + tile + 1];
@@ -83,8 +94,21 @@ render_fwd_kernel(RasterDims d, RasterWs ws, const float *__restrict__ bg,
         if ((int)threadIdx.x < cnt) {
             const uint32_t id = ws.ids[start + c0 + threadIdx.x];
             const float4 *src = reinterpret_cast<const float4 *>(rec_base + (size_t)id * GA_REC_F);
-#pragma unroll
-            for (int q = 0; q < 6; q++) s_rec[q][threadIdx.x] = __ldg(src + q);
+            const float4 a = __ldg(src), b = __ldg(src + 1), c = __ldg(src + 2);
+            const float4 nr = __ldg(src + 3), bb = __ldg(src + 4), gb = __ldg(src + 5);
+            // Tu = a.xyz, Tv = (a.w,b.x,b.y), Tw = (b.z,b.w,c.x), xy = (c.y,c.z), opacity = c.w
+            const float k0 = oxf * b.z - a.x, k1 = oxf * b.w - a.y, k2 = oxf * c.x - a.z;
+            const float l0 = oyf * b.z - a.w, l1 = oyf * b.w - b.x, l2 = oyf * c.x - b.y;
+            const float Cx = k1 * l2 - k2 * l1, Cy = k2 * l0 - k0 * l2, Cz = k0 * l1 - k1 * l0;
+            const float Ax = b.w * l2 - c.x * l1, Ay = c.x * l0 - b.z * l2, Az = b.z * l1 - b.w * l0;
+            const float Bx = k1 * c.x - k2 * b.w, By = k2 * b.z - k0 * c.x, Bz = k0 * b.w - k1 * b.z;
+            s_rec[0][threadIdx.x] = make_float4(Cx, Cy, Cz, Ax);
+            s_rec[1][threadIdx.x] = make_float4(Ay, Az, Bx, By);
+            s_rec[2][threadIdx.x] = make_float4(Bz, b.z, b.w, c.x);
+            s_rec[3][threadIdx.x] = make_float4(c.y - oxf, c.z - oyf, c.w, 0.f);
+            s_rec[4][threadIdx.x] = make_float4(bb.x - oxf, bb.y - oxf, bb.z - oyf, bb.w - oyf);
+            s_rec[5][threadIdx.x] = nr;
+            s_rec[6][threadIdx.x] = gb;
         }
         __syncthreads();
         for (int g0 = 0; g0 < cnt; g0 += 32) {
@@ -99,27 +123,37 @@ render_fwd_kernel(RasterDims d, RasterWs ws, const float *__restrict__ bg,
             while (mask) {
                 const int jj = g0 + __ffs(mask) - 1;
                 mask &= mask - 1;
-                const float4 a = s_rec[0][jj], b = s_rec[1][jj], c = s_rec[2][jj];
-                PixelGeom pg;
-                float k0, k1, k2, l0, l1, l2;
-                bool ok = !done && eval_pair(a, b, c, pfx, pfy, pg, k0, k1, k2, l0, l1, l2);
+                const float4 f0 = s_rec[0][jj], f1 = s_rec[1][jj], f2 = s_rec[2][jj], f3 = s_rec[3][jj];
+                const float p0 = f0.x + dxf * f0.w + dyf * f1.z;
+                const float p1 = f0.y + dxf * f1.x + dyf * f1.w;
+                const float p2 = f0.z + dxf * f1.y + dyf * f2.x;
+                const float ip = __fdividef(1.0f, p2);
+                const float s0 = p0 * ip, s1 = p1 * ip;
+                const float rho3d = s0 * s0 + s1 * s1;
+                const float ddx = f3.x - dxf, ddy = f3.y - dyf;
+                const float rho2d = GA_FILTER_INV_SQUARE * (ddx * ddx + ddy * ddy);
+                const float rho = fminf(rho3d, rho2d);
+                const float depth = (rho3d <= rho2d) ? (s0 * f2.y + s1 * f2.z) + f2.w : f2.w;
+                // power = -0.5*rho > 0 never happens for rho >= 0; NaN rho (p2 == 0) fails the alpha test
+                const float alpha = fminf(0.99f, f3.z * __expf(-0.5f * rho));
+                bool ok = !done && p2 != 0.0f && depth >= GA_NEAR_N && alpha >= 1.0f / 255.0f;
                 float test_T = 0.f;
                 if (ok) {
-                    test_T = T * (1 - pg.alpha);
+                    test_T = T * (1 - alpha);
                     if (test_T < 0.0001f) { done = true; ok = false; }
                 }
                 if (__any_sync(0xffffffffu, ok)) {
-                    const float4 nr = s_rec[3][jj], gb = s_rec[5][jj];
+                    const float4 nr = s_rec[5][jj], gb = s_rec[6][jj];
                     if (ok) {
                         const int contributor = c0 + jj + 1;
-                        const float w = pg.alpha * T;
+                        const float w = alpha * T;
                         const float A = 1 - T;
-                        const float m = GA_FAR_N / (GA_FAR_N - GA_NEAR_N) * (1 - GA_NEAR_N / pg.depth);
+                        const float m = GA_FAR_N / (GA_FAR_N - GA_NEAR_N) * (1 - GA_NEAR_N / depth);
                         dist += (m * m * A + M2 - 2 * m * M1) * w;
-                        Dacc += pg.depth * w;
+                        Dacc += depth * w;
                         M1 += m * w;
                         M2 += m * m * w;
-                        if (T > 0.5f) { median_depth = pg.depth; median_contributor = contributor; }
+                        if (T > 0.5f) { median_depth = depth; median_contributor = contributor; }
                         N0 += nr.x * w; N1 += nr.y * w; N2 += nr.z * w;
                         C0 += nr.w * w; C1 += gb.x * w; C2 += gb.y * w;
                         T = test_T;
@@ -321,13 +355,45 @@ render_bwd_kernel(RasterDims d, RasterWs ws, const float *__restrict__ bg,
                     }
                     g[14] = G * dL_dalpha;
                 }
+                // recursive-halving reduction of the 18 components over 32 lanes in
+                // 9+5+3+2+1 = 20 exchanges (a butterfly per component would take 90):
+                // each level halves the component set a lane is responsible for.
+                {
+                    const bool u4 = lane & 16, u3 = lane & 8, u2 = lane & 4, u1 = lane & 2, u0 = lane & 1;
+                    float a9[10];
 #pragma unroll
-                for (int f = 0; f < GA_GRAD_F; f++) g[f] = warp_sum(g[f]);
-                if (lane < GA_GRAD_F) {
-                    float v = g[0];
+                    for (int i = 0; i < 9; i++) {
+                        const float keep = u4 ? g[9 + i] : g[i], send = u4 ? g[i] : g[9 + i];
+                        a9[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+                    }
+                    a9[9] = 0.f;
+                    float b5[6];
 #pragma unroll
-                    for (int f = 1; f < GA_GRAD_F; f++) if (lane == f) v = g[f];
-                    atomicAdd(&s_acc[jj][lane], v);
+                    for (int i = 0; i < 5; i++) {
+                        const float keep = u3 ? a9[5 + i] : a9[i], send = u3 ? a9[i] : a9[5 + i];
+                        b5[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+                    }
+                    b5[5] = 0.f;
+                    float c3[4];
+#pragma unroll
+                    for (int i = 0; i < 3; i++) {
+                        const float keep = u2 ? b5[3 + i] : b5[i], send = u2 ? b5[i] : b5[3 + i];
+                        c3[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+                    }
+                    c3[3] = 0.f;
+                    float d2[2];
+#pragma unroll
+                    for (int i = 0; i < 2; i++) {
+                        const float keep = u1 ? c3[2 + i] : c3[i], send = u1 ? c3[i] : c3[2 + i];
+                        d2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+                    }
+                    const float keep = u0 ? d2[1] : d2[0], send = u0 ? d2[0] : d2[1];
+                    const float tot = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+                    const int i4 = (u0 ? 1 : 0) + (u1 ? 2 : 0);          // index inside the 3-group
+                    const int i3 = i4 + (u2 ? 3 : 0);                    // inside the 5-group
+                    const int i2 = i3 + (u3 ? 5 : 0);                    // inside the 9-group
+                    const int comp = i2 + (u4 ? 9 : 0);
+                    if (i4 < 3 && i3 < 5 && i2 < 9) atomicAdd(&s_acc[jj][comp], tot);
                 }
                 if (lane == 0) s_touched[jj] = 1;
             }
