@@ -92,6 +92,81 @@ int ga_raster_backward(const float *gauss13, int batch, int P, int views,
                        void *scratch, size_t scratch_bytes,
                        float *grad_gauss13, void *stream);
 
+/*
+ * ---------------------------------------------------------------------------
+ * Part 2: DiT denoiser forward (bf16 tensor-core path, fp32 residual stream).
+ * Replaces, for DiT_I23D_PCD_PixelArt_noclip[_clay_stage2].forward
+ * (/root/reference/dit/dit_i23d.py:511-567,707-750) and its block
+ * ImageCondDiTBlockPixelArtRMSNormClayLRM.forward
+ * (/root/reference/dit/dit_models_xformers.py:765-787), the cuBLAS nn.Linear
+ * calls, xformers.ops.memory_efficient_attention
+ * (/root/reference/vit/vision_transformer.py:297,
+ * /root/reference/ldm/modules/attention.py:538-546), xformers FusedMLP
+ * (/root/reference/dit/dit_models_xformers.py:281-286) and the RMSNorm /
+ * modulate / gate / residual elementwise launches around them.
+ * ---------------------------------------------------------------------------
+ */
+
+/* Epilogues fused into the tcgen05 GEMM  C[M,N] = A[M,K] * W[N,K]^T (+ bias). */
+#define GA_EPI_BF16            0   /* out bf16 [M, ld_out]                                   */
+#define GA_EPI_GELU_BF16       1   /* out bf16 = gelu_erf(acc + bias)   (FusedMLP first half) */
+#define GA_EPI_F32             2   /* out fp32 [M, ld_out]                                   */
+#define GA_EPI_RESID_GATE_F32  3   /* out fp32 [M, ld_out] += gate[m / rows_per_batch, n] * (acc + bias)   */
+#define GA_EPI_HEADS           4   /* split columns "(K H 64)" into heads: per-head RMSNorm on q/k, write
+                                      Q,K [B,H,tok_pitch,64] and V transposed [B,H,64,tok_pitch] (bf16) */
+
+typedef struct GaGemmEpilogue {
+    int mode;
+    const float *bias;        /* [N] or NULL */
+    void *out;                /* modes 0-3 */
+    int ld_out;
+    const float *gate;        /* mode 3: [batch, gate_ld] (already offset to the gate chunk) or NULL (= 1) */
+    int gate_ld;
+    int rows_per_batch;       /* tokens per batch item (modes 3, 4) */
+    void *q, *k, *vt;         /* mode 4 outputs (any may be NULL when that part is absent) */
+    const float *qn_w, *kn_w; /* per-head RMSNorm weights [64] (NULL = no norm) */
+    int heads;
+    int first_part;           /* mode 4: 0 when columns start with q, 1 when they start with k (cross-attn k|v) */
+    int tok_pitch;            /* padded token count of the Q/K rows and Vt columns (multiple of 128) */
+    float eps;
+} GaGemmEpilogue;
+
+/* A [M, lda] bf16 row-major, W [N, ldw] bf16 row-major (nn.Linear weight), K contiguous in both.
+ * block_n in {64, 128, 256} selects the 128 x block_n output tile.  lda, ldw multiples of 8. */
+int ga_gemm_bf16_tn(const void *A, int lda, const void *W, int ldw, int M, int N, int K,
+                    const GaGemmEpilogue *epi, int block_n, void *stream);
+
+/* softmax(Q K^T * softmax_scale) V, head_dim 64.  Q [B*H, pitch_q, 64], K [B*H, pitch_k, 64],
+ * Vt [B*H, 64, pitch_k] (bf16, padding beyond Nk must be finite); out [B, Nq, H*64] bf16.
+ * pitch_k must be a multiple of 128. */
+int ga_attention_bf16(const void *Q, const void *K, const void *Vt, void *out, int batch, int heads,
+                      int Nq, int Nk, int pitch_q, int pitch_k, float softmax_scale, void *stream);
+
+/* out_bf16[r,:] = RMSNorm(x[r,:]; eps) * w [* (1 + scale[b,:]) + shift[b,:]], b = r / rows_per_batch;
+ * shift/scale both NULL or both set, rows mod_ld apart. */
+int ga_rmsnorm_modulate(const float *x, const float *w, const float *shift, const float *scale,
+                        int mod_ld, int rows_per_batch, void *out_bf16, int R, int D, float eps, void *stream);
+
+/* y[b,n] (+)= act_out(bias[n] + sum_k act_in(x[b,k]) W[n,k]);  rows <= 16; act: 0 none, 1 SiLU. */
+int ga_linear_small(const float *x, const float *W, const float *bias, float *y, int rows, int N, int K,
+                    int act_in, int act_out, int accumulate, void *stream);
+int ga_timestep_sinusoid(const float *t, float *out, int rows, int dim, void *stream);
+int ga_layernorm_rows(const float *x, const float *w, const float *b, float *y, int R, int D, float eps, void *stream);
+/* mod[l,b,e] = tables[l,e] + t0[b, e % t0_ld], e in [0, JD) */
+int ga_add_tables(const float *tables, const float *t0, float *mod, int L, int rows, int JD, int t0_ld, void *stream);
+/* h = gelu_tanh(W1 [xin2 | xin] + b1) -> bf16 [R, D] (token embedder, first layer) */
+int ga_embed_fc1(const float *xin, int Cx, const float *xin2, int C2, const float *W1, const float *b1,
+                 void *h_bf16, int R, int D, void *stream);
+/* NeRF positional encoding of xyz (63 features, padded to 64) -> bf16 [R, 64] */
+int ga_xyz_posenc(const float *xyz, void *out_bf16, int R, void *stream);
+/* y[r,c] = bias[c] + sum_d (LayerNorm(x[r])[d] (1 + scale[b,d]) + shift[b,d]) W[c,d]; mod [B,2,D]; Cout <= 16 */
+int ga_final_layer(const float *x, const float *mod, const float *W, const float *bias, float *y, int R,
+                   int D, int Cout, int rows_per_batch, float eps, void *stream);
+/* eps [2*half] = (cond | uncond) -> h = u + s (c - u) written to both halves of out */
+int ga_cfg_combine(const float *eps, float *out, int64_t half_elems, float cfg_scale, void *stream);
+int ga_axpy(float *x, const float *v, float a, int64_t n, void *stream);          /* x += a v */
+int ga_f32_to_bf16(const float *x, void *y, int64_t n, void *stream);
+
 /* Measurement aid: when enabled, cudaEvents are recorded around every kernel
  * stage of the next forward/backward; ga_profile_read synchronises on them and
  * returns per-stage milliseconds: [0] preprocess, [1] binning, [2] render fwd,

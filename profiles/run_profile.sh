@@ -1,10 +1,9 @@
 #!/bin/bash
 # Profiling recipe (run under gpurun on one B200).  Outputs land in gpurun_out/.
-set -x
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/gpu.csv
-python bench.py --steps 10 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err
-tail -c 3000 gpurun_out/bench.json
+python bench.py --steps 50 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err
+tail -c 2500 gpurun_out/bench.json; tail -5 gpurun_out/bench.err
 # every launch with its device time (cold-cache, serialised: compare SHARES)
 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv \
     --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 > gpurun_out/b_ncu.log 2>&1
