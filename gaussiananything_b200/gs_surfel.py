@@ -37,7 +37,10 @@ class GaussianRenderer2DGS:
             float(scale_modifier))
         alphas = allmap[:, :, 1:2]
         # normals: camera -> world, (n^T @ view[:3,:3].T) per pixel (reference :125-128)
-        normals = torch.einsum('bvchw,bvdc->bvdhw', allmap[:, :, 2:5], cam_view[:, :, :3, :3])
+        R = cam_view[:, :, :3, :3]
+        n = allmap[:, :, 2:5]
+        normals = torch.stack([n[:, :, 0] * R[:, :, d, 0, None, None] + n[:, :, 1] * R[:, :, d, 1, None, None]
+                               + n[:, :, 2] * R[:, :, d, 2, None, None] for d in range(3)], dim=2)
         depths = torch.nan_to_num(allmap[:, :, 5:6], 0, 0)        # median depth, depth_ratio = 1
         dists = allmap[:, :, 6:7]
         images = color.clamp(0, 1)
