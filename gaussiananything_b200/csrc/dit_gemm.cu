@@ -5,11 +5,12 @@
 // /root/reference/vit/vision_transformer.py:215-303 and
 // /root/reference/ldm/modules/attention.py:484-561.
 //
-// One CTA computes one 128 x BN output tile:
+// Persistent kernel, one CTA per SM looping over 128 x BN output tiles:
 //   warp 0   : TMA producer  (cp.async.bulk.tensor, 128B-swizzled K-major tiles)
 //   warp 1   : TMEM allocator + single-thread tcgen05.mma issuer
-//   warps 2-5: epilogue, one accumulator row per thread (tcgen05.ld 32x32b)
-// smem ring of kStages {A 128x64, W BNx64} bf16 tiles, full/empty mbarriers.
+//   warps 2-9: epilogue, one accumulator row per thread (tcgen05.ld 32x32b), half the columns per warp
+// smem ring of kStages {A 128x64, W BNx64} bf16 tiles with full/empty mbarriers; the TMEM accumulator is
+// double buffered (acc_full/acc_empty) so the epilogue of one tile overlaps the main loop of the next.
 #include "../../include/ga_b200.h"
 #include "sm100_ptx.cuh"
 
@@ -18,16 +19,35 @@ using namespace sm100;
 namespace {
 
 constexpr int BM = 128, BK = 64;
-constexpr int kThreads = 192;
+constexpr int kEpiWarps = 8;
+constexpr int kThreads = 64 + 32 * kEpiWarps;          // TMA warp + MMA warp + 8 epilogue warps
 
 template <int BN> struct GemmCfg {
-    static constexpr int kStages = (BN >= 256) ? 4 : 4;
+    static constexpr int kStages = (BN >= 256) ? 4 : 6;
     static constexpr int kABytes = BM * BK * 2;
     static constexpr int kBBytes = BN * BK * 2;
     static constexpr int kSmem = kStages * (kABytes + kBBytes) + 1024;
+    static constexpr int kTmemCols = 2 * BN;           // double-buffered accumulator
 };
 
-__device__ __forceinline__ float gelu_erf(float v) { return 0.5f * v * (1.0f + erff(v * 0.70710678118654752f)); }
+// exact-erf GELU to ~3e-7 (Abramowitz-Stegun 7.1.28: erf x = 1 - (1 + a1 x + .. + a6 x^6)^-16), 1 MUFU + ~16 FP32
+// ops per element; the library erff() costs about twice that and would make the GELU epilogue slower than the MMAs.
+__device__ __forceinline__ float gelu_erf(float v)
+{
+    const float x = fabsf(v) * 0.70710678118654752f;
+    float p = 0.0000430638f;
+    p = fmaf(p, x, 0.0002765672f);
+    p = fmaf(p, x, 0.0001520143f);
+    p = fmaf(p, x, 0.0092705272f);
+    p = fmaf(p, x, 0.0422820123f);
+    p = fmaf(p, x, 0.0705230784f);
+    p = fmaf(p, x, 1.0f);
+    p = p * p; p = p * p; p = p * p; p = p * p;
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(p));
+    const float erf_abs = 1.0f - r;
+    return 0.5f * v * (1.0f + copysignf(erf_abs, v));
+}
 
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b)
 {
@@ -35,89 +55,59 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b)
     return *reinterpret_cast<uint32_t *>(&h);
 }
 
-// epilogue for 64 consecutive columns [n, n+64) of one row (v[] = accumulator)
-__device__ __forceinline__ void epilogue64(const GaGemmEpilogue &ep, int m, int n, int M, int N, float (&v)[64])
+// epilogue for 32 consecutive columns [n, n+32) of one row (v[] = accumulator + bias already added)
+__device__ __forceinline__ void epilogue32(const GaGemmEpilogue &ep, int m, int n, int N, float (&v)[32])
 {
-    if (m >= M || n >= N) return;
-    if (ep.bias) {
-#pragma unroll
-        for (int i = 0; i < 64; i++) v[i] += (n + i < N) ? __ldg(ep.bias + n + i) : 0.f;
-    }
-    const bool full = (n + 64 <= N);
+    const bool full = (n + 32 <= N);
     switch (ep.mode) {
     case GA_EPI_BF16:
     case GA_EPI_GELU_BF16: {
         if (ep.mode == GA_EPI_GELU_BF16) {
 #pragma unroll
-            for (int i = 0; i < 64; i++) v[i] = gelu_erf(v[i]);
+            for (int i = 0; i < 32; i++) v[i] = gelu_erf(v[i]);
         }
         __nv_bfloat16 *dst = reinterpret_cast<__nv_bfloat16 *>(ep.out) + (size_t)m * ep.ld_out + n;
         if (full && (ep.ld_out % 8) == 0) {
             uint4 *d4 = reinterpret_cast<uint4 *>(dst);
 #pragma unroll
-            for (int i = 0; i < 8; i++)
+            for (int i = 0; i < 4; i++)
                 d4[i] = make_uint4(pack_bf16(v[8 * i], v[8 * i + 1]), pack_bf16(v[8 * i + 2], v[8 * i + 3]),
                                    pack_bf16(v[8 * i + 4], v[8 * i + 5]), pack_bf16(v[8 * i + 6], v[8 * i + 7]));
         } else {
-            for (int i = 0; i < 64 && n + i < N; i++) dst[i] = __float2bfloat16(v[i]);
+#pragma unroll
+            for (int i = 0; i < 32; i++) if (n + i < N) dst[i] = __float2bfloat16(v[i]);
         }
         break;
     }
     case GA_EPI_F32: {
         float *dst = reinterpret_cast<float *>(ep.out) + (size_t)m * ep.ld_out + n;
-        for (int i = 0; i < 64 && n + i < N; i++) dst[i] = v[i];
+        if (full && (ep.ld_out % 4) == 0) {
+            float4 *d4 = reinterpret_cast<float4 *>(dst);
+#pragma unroll
+            for (int i = 0; i < 8; i++) d4[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 32; i++) if (n + i < N) dst[i] = v[i];
+        }
         break;
     }
     case GA_EPI_RESID_GATE_F32: {
         // x[m, n] += gate[b, n] * (acc + bias)
         float *dst = reinterpret_cast<float *>(ep.out) + (size_t)m * ep.ld_out + n;
         const float *g = ep.gate ? ep.gate + (size_t)(m / ep.rows_per_batch) * ep.gate_ld + n : nullptr;
-        if (full && (ep.ld_out % 4) == 0) {
+        if (full && (ep.ld_out % 4) == 0 && (!g || (ep.gate_ld % 4) == 0)) {
             float4 *d4 = reinterpret_cast<float4 *>(dst);
+            const float4 *g4 = reinterpret_cast<const float4 *>(g);
 #pragma unroll
-            for (int i = 0; i < 16; i++) {
+            for (int i = 0; i < 8; i++) {
                 float4 x = d4[i];
-                const float g0 = g ? __ldg(g + 4 * i) : 1.f, g1 = g ? __ldg(g + 4 * i + 1) : 1.f;
-                const float g2 = g ? __ldg(g + 4 * i + 2) : 1.f, g3 = g ? __ldg(g + 4 * i + 3) : 1.f;
-                x.x += g0 * v[4 * i]; x.y += g1 * v[4 * i + 1]; x.z += g2 * v[4 * i + 2]; x.w += g3 * v[4 * i + 3];
+                const float4 gg = g ? __ldg(g4 + i) : make_float4(1.f, 1.f, 1.f, 1.f);
+                x.x += gg.x * v[4 * i]; x.y += gg.y * v[4 * i + 1]; x.z += gg.z * v[4 * i + 2]; x.w += gg.w * v[4 * i + 3];
                 d4[i] = x;
             }
         } else {
-            for (int i = 0; i < 64 && n + i < N; i++) dst[i] += (g ? __ldg(g + i) : 1.f) * v[i];
-        }
-        break;
-    }
-    case GA_EPI_HEADS: {
-        // 64 columns == one attention head of q, k or v.  Column layout "(K H D)":
-        // which = n / inner, head = (n % inner) / 64   (vit/vision_transformer.py:191, 255)
-        const int inner = ep.heads * 64;
-        const int which = n / inner + ep.first_part;        // 0 = q, 1 = k, 2 = v
-        const int head = (n % inner) / 64;
-        const int b = m / ep.rows_per_batch, t = m % ep.rows_per_batch;
-        const size_t bh = (size_t)b * ep.heads + head;
-        if (which <= 1) {
-            // per-head RMSNorm (dit/norm.py:27-40, eps 1e-5), fp32, then * weight
-            const float *w = which == 0 ? ep.qn_w : ep.kn_w;
-            if (w) {
-                float ss = 0.f;
 #pragma unroll
-                for (int i = 0; i < 64; i++) ss += v[i] * v[i];
-                const float r = rsqrtf(ss * (1.0f / 64.0f) + ep.eps);
-#pragma unroll
-                for (int i = 0; i < 64; i++) v[i] = v[i] * r * __ldg(w + i);
-            }
-            __nv_bfloat16 *base = reinterpret_cast<__nv_bfloat16 *>(which == 0 ? ep.q : ep.k);
-            uint4 *d4 = reinterpret_cast<uint4 *>(base + (bh * ep.tok_pitch + t) * 64);
-#pragma unroll
-            for (int i = 0; i < 8; i++)
-                d4[i] = make_uint4(pack_bf16(v[8 * i], v[8 * i + 1]), pack_bf16(v[8 * i + 2], v[8 * i + 3]),
-                                   pack_bf16(v[8 * i + 4], v[8 * i + 5]), pack_bf16(v[8 * i + 6], v[8 * i + 7]));
-        } else {
-            // V is stored transposed per head, [B, H, 64, tok_pitch], so that P*V is a
-            // K-major x K-major tcgen05 contraction (keys contiguous)
-            __nv_bfloat16 *base = reinterpret_cast<__nv_bfloat16 *>(ep.vt) + bh * 64 * ep.tok_pitch + t;
-#pragma unroll
-            for (int i = 0; i < 64; i++) base[(size_t)i * ep.tok_pitch] = __float2bfloat16(v[i]);
+            for (int i = 0; i < 32; i++) if (n + i < N) dst[i] += (g ? __ldg(g + i) : 1.f) * v[i];
         }
         break;
     }
@@ -125,6 +115,63 @@ __device__ __forceinline__ void epilogue64(const GaGemmEpilogue &ep, int m, int 
     }
 }
 
+// HEADS epilogue for one head (64 columns [n, n+64)): two TMEM passes keep the live set at 32 values.
+//   which = n / inner (+ first_part): 0 q, 1 k, 2 v ; head = (n % inner) / 64   ("(K H D)" column layout,
+//   vit/vision_transformer.py:191,255).  q/k: per-head RMSNorm (dit/norm.py:27-40), fp32, then * weight.
+__device__ __forceinline__ void epilogue_head(const GaGemmEpilogue &ep, uint32_t taddr, int m, int n, int M)
+{
+    const int inner = ep.heads * 64;
+    const int which = n / inner + ep.first_part;
+    const int head = (n % inner) / 64;
+    const int mm = m < M ? m : 0;
+    const int b = mm / ep.rows_per_batch, t = mm % ep.rows_per_batch;
+    const size_t bh = (size_t)b * ep.heads + head;
+    uint32_t r[32];
+    float rs = 1.0f;
+    const float *w = which == 0 ? ep.qn_w : (which == 1 ? ep.kn_w : nullptr);
+    if (w) {
+        float ss = 0.f;
+#pragma unroll
+        for (int h2 = 0; h2 < 2; h2++) {
+            tmem_ld_32x32b_x32(taddr + h2 * 32, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; i++) {
+                const float x = __uint_as_float(r[i]) + (ep.bias ? __ldg(ep.bias + n + h2 * 32 + i) : 0.f);
+                ss += x * x;
+            }
+        }
+        rs = rsqrtf(ss * (1.0f / 64.0f) + ep.eps);
+    }
+#pragma unroll
+    for (int h2 = 0; h2 < 2; h2++) {
+        tmem_ld_32x32b_x32(taddr + h2 * 32, r);
+        tmem_ld_wait();
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 32; i++) {
+            v[i] = __uint_as_float(r[i]) + (ep.bias ? __ldg(ep.bias + n + h2 * 32 + i) : 0.f);
+            if (w) v[i] = v[i] * rs * __ldg(w + h2 * 32 + i);
+        }
+        if (m >= M) continue;
+        if (which <= 1) {
+            __nv_bfloat16 *base = reinterpret_cast<__nv_bfloat16 *>(which == 0 ? ep.q : ep.k);
+            uint4 *d4 = reinterpret_cast<uint4 *>(base + (bh * ep.tok_pitch + t) * 64 + h2 * 32);
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+                d4[i] = make_uint4(pack_bf16(v[8 * i], v[8 * i + 1]), pack_bf16(v[8 * i + 2], v[8 * i + 3]),
+                                   pack_bf16(v[8 * i + 4], v[8 * i + 5]), pack_bf16(v[8 * i + 6], v[8 * i + 7]));
+        } else {
+            // V stored transposed per head, [B, H, 64, tok_pitch]: P*V becomes a K-major x K-major contraction
+            __nv_bfloat16 *base = reinterpret_cast<__nv_bfloat16 *>(ep.vt) + (bh * 64 + h2 * 32) * ep.tok_pitch + t;
+#pragma unroll
+            for (int i = 0; i < 32; i++) base[(size_t)i * ep.tok_pitch] = __float2bfloat16(v[i]);
+        }
+    }
+}
+
+// Persistent: grid = min(#tiles, #SMs); every role loops over the CTA's tiles.  The TMEM accumulator is double
+// buffered (2*BN columns), so the epilogue of tile i overlaps the TMA/MMA main loop of tile i+1.
 template <int BN>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
@@ -132,14 +179,15 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
 {
     using Cfg = GemmCfg<BN>;
     extern __shared__ uint8_t smem_raw[];
-    __shared__ uint64_t full_bar[Cfg::kStages], empty_bar[Cfg::kStages], acc_bar;
+    __shared__ uint64_t full_bar[Cfg::kStages], empty_bar[Cfg::kStages], acc_full[2], acc_empty[2];
     __shared__ uint32_t tmem_slot;
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t *smem_a = smem, *smem_b = smem + Cfg::kStages * Cfg::kABytes;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
     const int nk = (K + BK - 1) / BK;
+    const int num_m = (M + BM - 1) / BM, num_n = (N + BN - 1) / BN;
+    const int tiles = num_m * num_n;
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tma_a);
@@ -148,11 +196,11 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     if (warp == 1) {
         if (lane == 0) {
             for (int s = 0; s < Cfg::kStages; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-            mbar_init(&acc_bar, 1);
+            for (int a = 0; a < 2; a++) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], kEpiWarps); }
             fence_barrier_init();
         }
         __syncwarp();
-        tmem_alloc<BN>(&tmem_slot);
+        tmem_alloc<Cfg::kTmemCols>(&tmem_slot);
     }
     tc_fence_before();
     __syncthreads();
@@ -161,55 +209,84 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
 
     if (warp == 0) {
         if (elect_one()) {
-            for (int kb = 0; kb < nk; kb++) {
-                const int s = kb % Cfg::kStages;
-                const uint32_t ph = (kb / Cfg::kStages) & 1;
-                mbar_wait(&empty_bar[s], ph ^ 1);
-                mbar_expect_tx(&full_bar[s], Cfg::kABytes + Cfg::kBBytes);
-                tma_load_2d(smem_a + s * Cfg::kABytes, &tma_a, &full_bar[s], kb * BK, m0);
-                tma_load_2d(smem_b + s * Cfg::kBBytes, &tma_b, &full_bar[s], kb * BK, n0);
+            int it = 0;
+            for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+                const int m0 = (tile % num_m) * BM, n0 = (tile / num_m) * BN;
+                for (int kb = 0; kb < nk; kb++, it++) {
+                    const int s = it % Cfg::kStages;
+                    const uint32_t ph = (it / Cfg::kStages) & 1;
+                    mbar_wait(&empty_bar[s], ph ^ 1);
+                    mbar_expect_tx(&full_bar[s], Cfg::kABytes + Cfg::kBBytes);
+                    tma_load_2d(smem_a + s * Cfg::kABytes, &tma_a, &full_bar[s], kb * BK, m0);
+                    tma_load_2d(smem_b + s * Cfg::kBBytes, &tma_b, &full_bar[s], kb * BK, n0);
+                }
             }
         }
     } else if (warp == 1) {
         if (elect_one()) {
             constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
-            for (int kb = 0; kb < nk; kb++) {
-                const int s = kb % Cfg::kStages;
-                const uint32_t ph = (kb / Cfg::kStages) & 1;
-                mbar_wait(&full_bar[s], ph);
+            int it = 0, lt = 0;
+            for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, lt++) {
+                const int a = lt & 1;
+                mbar_wait(&acc_empty[a], ((lt >> 1) & 1) ^ 1);
                 tc_fence_after();
-                const uint64_t ad = umma_desc_k_sw128(smem_u32(smem_a + s * Cfg::kABytes));
-                const uint64_t bd = umma_desc_k_sw128(smem_u32(smem_b + s * Cfg::kBBytes));
+                const uint32_t tacc = tmem + (uint32_t)(a * BN);
+                for (int kb = 0; kb < nk; kb++, it++) {
+                    const int s = it % Cfg::kStages;
+                    mbar_wait(&full_bar[s], (it / Cfg::kStages) & 1);
+                    tc_fence_after();
+                    const uint64_t ad = umma_desc_k_sw128(smem_u32(smem_a + s * Cfg::kABytes));
+                    const uint64_t bd = umma_desc_k_sw128(smem_u32(smem_b + s * Cfg::kBBytes));
 #pragma unroll
-                for (int k = 0; k < BK / 16; k++)
-                    umma_bf16_ss(tmem, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, (kb | k) != 0);
-                umma_commit(&empty_bar[s]);     // frees the smem stage when these MMAs retire
+                    for (int k = 0; k < BK / 16; k++)
+                        umma_bf16_ss(tacc, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+                    umma_commit(&empty_bar[s]);     // frees the smem stage when these MMAs retire
+                }
+                umma_commit(&acc_full[a]);          // accumulator of this tile complete
             }
-            umma_commit(&acc_bar);              // accumulator complete
         }
     } else {
-        const int q = warp & 3;                 // TMEM lane quarter this warp may access
+        const int ew = warp - 2;
+        const int q = warp & 3;                     // TMEM lane quarter this warp may access
+        const int chalf = ew >> 2;                  // which half of the BN columns this warp drains
         const int row = q * 32 + lane;
-        mbar_wait(&acc_bar, 0);
-        tc_fence_after();
-        const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
+        int lt = 0;
+        for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, lt++) {
+            const int m0 = (tile % num_m) * BM, n0 = (tile / num_m) * BN;
+            const int a = lt & 1;
+            mbar_wait(&acc_full[a], (lt >> 1) & 1);
+            tc_fence_after();
+            const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * BN);
+            const int m = m0 + row;
+            if (ep.mode == GA_EPI_HEADS) {
 #pragma unroll 1
-        for (int c = 0; c < BN; c += 64) {
-            uint32_t r0[32], r1[32];
-            tmem_ld_32x32b_x32(trow + c, r0);
-            tmem_ld_32x32b_x32(trow + c + 32, r1);
-            tmem_ld_wait();
-            float v[64];
+                for (int c = chalf * (BN / 2); c < (chalf + 1) * (BN / 2); c += 64)
+                    if (n0 + c < N) epilogue_head(ep, trow + c, m, n0 + c, M);
+            } else {
+#pragma unroll 1
+                for (int c = chalf * (BN / 2); c < (chalf + 1) * (BN / 2); c += 32) {
+                    if (n0 + c >= N) break;                       // warp-uniform
+                    uint32_t r[32];
+                    tmem_ld_32x32b_x32(trow + c, r);
+                    tmem_ld_wait();
+                    if (m < M) {
+                        float v[32];
 #pragma unroll
-            for (int i = 0; i < 32; i++) { v[i] = __uint_as_float(r0[i]); v[32 + i] = __uint_as_float(r1[i]); }
-            epilogue64(ep, m0 + row, n0 + c, M, N, v);
+                        for (int i = 0; i < 32; i++)
+                            v[i] = __uint_as_float(r[i]) + ((ep.bias && n0 + c + i < N) ? __ldg(ep.bias + n0 + c + i) : 0.f);
+                        epilogue32(ep, m, n0 + c, N, v);
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[a]);
         }
-        tc_fence_before();
     }
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc<BN>(tmem);
+        tmem_dealloc<Cfg::kTmemCols>(tmem);
     }
 }
 
@@ -262,7 +339,15 @@ static int launch_gemm(const CUtensorMap &ta, const CUtensorMap &tb, const GaGem
         if (e != cudaSuccess) return (int)e;
         attr_set = true;
     }
-    dim3 grid((M + BM - 1) / BM, (N + BN - 1) / BN);
+    static int num_sms = 0;
+    if (!num_sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+        if (num_sms <= 0) num_sms = 148;
+    }
+    const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
+    dim3 grid(tiles < num_sms ? tiles : num_sms);
     gemm_bf16_tn_kernel<BN><<<grid, kThreads, Cfg::kSmem, s>>>(ta, tb, ep, M, N, K);
     return (int)cudaGetLastError();
 }
@@ -271,7 +356,7 @@ extern "C" int ga_gemm_bf16_tn(const void *A, int lda, const void *W, int ldw, i
                                const GaGemmEpilogue *epi, int block_n, void *stream)
 {
     if (!A || !W || !epi || M <= 0 || N <= 0 || K <= 0) return GA_ERR_BADARG;
-    if (epi->mode == GA_EPI_HEADS && (N % 64 != 0 || epi->heads <= 0)) return GA_ERR_BADARG;
+    if (epi->mode == GA_EPI_HEADS && (N % 64 != 0 || epi->heads <= 0 || block_n < 128)) return GA_ERR_BADARG;
     if (block_n != 64 && block_n != 128 && block_n != 256) return GA_ERR_BADARG;
     CUtensorMap ta, tb;
     int rc = ga_make_tmap_bf16(&ta, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, BM);

@@ -361,7 +361,9 @@ class _DiTEngine:
         self._ctx_key = None
 
     # ---- launches
-    def _gemm(self, A, W, M, N, K, epi, st, bn=128):
+    def _gemm(self, A, W, M, N, K, epi, st, bn=None):
+        if bn is None:                       # wide outputs: 128x256 tiles halve the operand re-reads from L2
+            bn = 256 if N >= 2048 else 128
         _ck(self.L.ga_gemm_bf16_tn(_p(A), K, _p(W), K, M, N, K, C.byref(epi), bn, st), "ga_gemm_bf16_tn")
 
     def _epi(self, mode, **kw):
