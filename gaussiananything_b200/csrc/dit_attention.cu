@@ -15,8 +15,8 @@
 //   warps 2-5: softmax, one query row per thread: S from TMEM -> registers,
 //              online max/sum in the exp2 domain, P (bf16) -> smem, O_blk from
 //              TMEM accumulated in registers with the running rescale.
-// S and O_blk are double buffered in TMEM (2x128 + 2x64 columns) so the next
-// block's QK^T overlaps this block's softmax.
+// Two CTAs share an SM (97 KB smem, 256 TMEM columns each), so one CTA's MMAs / TMA loads overlap
+// the other's softmax; within a CTA the next block's QK^T is issued as soon as S has been read.
 #include "../../include/ga_b200.h"
 #include "sm100_ptx.cuh"
 
@@ -29,32 +29,42 @@ namespace {
 
 constexpr int AQ = 128, AK = 128, HD = 64;
 constexpr int kQBytes = AQ * HD * 2;            // 16 KB
-constexpr int kKBytes = AK * HD * 2;            // 16 KB
-constexpr int kVBytes = HD * AK * 2;            // 16 KB (two 64-key sub-tiles of 8 KB)
-constexpr int kPBytes = AQ * AK * 2;            // 32 KB (two 64-key sub-tiles of 16 KB)
-constexpr int kSmemAttn = kQBytes + 2 * kKBytes + 2 * kVBytes + 2 * kPBytes + 1024;
+constexpr int kKBytes = AK * HD * 2;            // 16 KB per stage, 2 stages
+constexpr int kVBytes = HD * AK * 2;            // 16 KB (two 64-key sub-tiles of 8 KB), 1 stage
+constexpr int kPBytes = AQ * AK * 2;            // 32 KB (two 64-key sub-tiles of 16 KB), 1 buffer
+constexpr int kSmemAttn = kQBytes + 2 * kKBytes + kVBytes + kPBytes + 1024;     // 97 KB -> 2 CTAs / SM
 constexpr int kAttnThreads = 192;
+constexpr uint32_t kTmemColsAttn = 256;         // S: 128 columns, O_blk: 64 columns; 2 CTAs share the SM's 512
 
 __device__ __forceinline__ uint32_t pack2(float a, float b)
 {
     __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t *>(&h);
 }
+__device__ __forceinline__ float ex2_fast(float x)
+{
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
 
-__global__ void __launch_bounds__(kAttnThreads, 1)
+// Two CTAs are co-resident per SM (97 KB smem, 256 TMEM columns, <=168 registers): while one CTA's softmax
+// warps keep the MUFU/FMA pipes busy, the other CTA's MMAs and TMA loads run -- the hardware interleaves the
+// two dependency chains, so the kernel needs no intra-CTA ping-pong.
+__global__ void __launch_bounds__(kAttnThreads, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_k,
                 const __grid_constant__ CUtensorMap tma_vt, __nv_bfloat16 *__restrict__ out,
                 const int Nq, const int Nk, const int pitch_q, const int pitch_k, const int heads,
                 const float scale_log2)
 {
     extern __shared__ uint8_t smem_raw[];
-    __shared__ uint64_t q_full, k_full[2], k_empty[2], v_full[2], v_empty[2], s_full[2], p_full[2], o_full[2];
+    __shared__ uint64_t q_full, k_full[2], k_empty[2], v_full, v_empty, s_full, p_full, o_full, o_empty;
     __shared__ uint32_t tmem_slot;
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t *sQ = smem;
     uint8_t *sK = sQ + kQBytes;
     uint8_t *sV = sK + 2 * kKBytes;
-    uint8_t *sP = sV + 2 * kVBytes;
+    uint8_t *sP = sV + kVBytes;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int bh = blockIdx.y;
@@ -67,22 +77,20 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
     if (warp == 1) {
         if (lane == 0) {
             mbar_init(&q_full, 1);
-            for (int s = 0; s < 2; s++) {
-                mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1);
-                mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1);
-                mbar_init(&s_full[s], 1); mbar_init(&o_full[s], 1);
-                mbar_init(&p_full[s], 128);
-            }
+            for (int s = 0; s < 2; s++) { mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1); }
+            mbar_init(&v_full, 1); mbar_init(&v_empty, 1);
+            mbar_init(&s_full, 1); mbar_init(&o_full, 1);
+            mbar_init(&p_full, 128); mbar_init(&o_empty, 128);
             fence_barrier_init();
         }
         __syncwarp();
-        tmem_alloc<512>(&tmem_slot);
+        tmem_alloc<kTmemColsAttn>(&tmem_slot);
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = tmem_slot;
-    const uint32_t tS[2] = {tmem, tmem + 128}, tO[2] = {tmem + 256, tmem + 320};
+    const uint32_t tS = tmem, tO = tmem + 128;
 
     if (warp == 0) {
         if (elect_one()) {
@@ -90,14 +98,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
             tma_load_2d(sQ, &tma_q, &q_full, 0, bh * pitch_q + q0);
             for (int j = 0; j < nb; j++) {
                 const int s = j & 1;
-                const uint32_t ph = (j >> 1) & 1;
-                mbar_wait(&k_empty[s], ph ^ 1);
+                mbar_wait(&k_empty[s], ((j >> 1) & 1) ^ 1);
                 mbar_expect_tx(&k_full[s], kKBytes);
                 tma_load_2d(sK + s * kKBytes, &tma_k, &k_full[s], 0, bh * pitch_k + j * AK);
-                mbar_wait(&v_empty[s], ph ^ 1);
-                mbar_expect_tx(&v_full[s], kVBytes);
-                tma_load_2d(sV + s * kVBytes, &tma_vt, &v_full[s], j * AK, bh * HD);
-                tma_load_2d(sV + s * kVBytes + kVBytes / 2, &tma_vt, &v_full[s], j * AK + 64, bh * HD);
+                mbar_wait(&v_empty, (j & 1) ^ 1);
+                mbar_expect_tx(&v_full, kVBytes);
+                tma_load_2d(sV, &tma_vt, &v_full, j * AK, bh * HD);
+                tma_load_2d(sV + kVBytes / 2, &tma_vt, &v_full, j * AK + 64, bh * HD);
             }
         }
     } else if (warp == 1) {
@@ -105,6 +112,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
             constexpr uint32_t idesc_s = umma_idesc_bf16(AQ, AK);
             constexpr uint32_t idesc_o = umma_idesc_bf16(AQ, HD);
             const uint64_t qd = umma_desc_k_sw128(smem_u32(sQ));
+            const uint64_t pd = umma_desc_k_sw128(smem_u32(sP));
+            const uint64_t vd = umma_desc_k_sw128(smem_u32(sV));
             mbar_wait(&q_full, 0);
             auto issue_s = [&](int j) {
                 const int s = j & 1;
@@ -113,29 +122,27 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
                 const uint64_t kd = umma_desc_k_sw128(smem_u32(sK + s * kKBytes));
 #pragma unroll
                 for (int k = 0; k < HD / 16; k++)
-                    umma_bf16_ss(tS[s], qd + (uint64_t)(2 * k), kd + (uint64_t)(2 * k), idesc_s, k != 0);
+                    umma_bf16_ss(tS, qd + (uint64_t)(2 * k), kd + (uint64_t)(2 * k), idesc_s, k != 0);
                 umma_commit(&k_empty[s]);
-                umma_commit(&s_full[s]);
+                umma_commit(&s_full);
             };
             issue_s(0);
             for (int j = 0; j < nb; j++) {
-                const int s = j & 1;
-                const uint32_t ph = (j >> 1) & 1;
-                if (j + 1 < nb) issue_s(j + 1);
-                mbar_wait(&p_full[s], ph);
-                mbar_wait(&v_full[s], ph);
+                const uint32_t ph = j & 1;
+                mbar_wait(&p_full, ph);                 // P_j staged; S_j has been consumed
+                if (j + 1 < nb) issue_s(j + 1);         // next QK^T overlaps this block's P*V and the O read-out
+                mbar_wait(&v_full, ph);
+                mbar_wait(&o_empty, ph ^ 1);            // softmax warps have read O_{j-1}
                 tc_fence_after();
-                const uint64_t pd = umma_desc_k_sw128(smem_u32(sP + s * kPBytes));
-                const uint64_t vd = umma_desc_k_sw128(smem_u32(sV + s * kVBytes));
 #pragma unroll
                 for (int kk = 0; kk < AK / 16; kk++) {
                     const uint64_t sub_p = (uint64_t)((kk >> 2) * ((kPBytes / 2) >> 4));
                     const uint64_t sub_v = (uint64_t)((kk >> 2) * ((kVBytes / 2) >> 4));
-                    umma_bf16_ss(tO[s], pd + sub_p + (uint64_t)(2 * (kk & 3)), vd + sub_v + (uint64_t)(2 * (kk & 3)),
+                    umma_bf16_ss(tO, pd + sub_p + (uint64_t)(2 * (kk & 3)), vd + sub_v + (uint64_t)(2 * (kk & 3)),
                                  idesc_o, kk != 0);
                 }
-                umma_commit(&v_empty[s]);
-                umma_commit(&o_full[s]);
+                umma_commit(&v_empty);
+                umma_commit(&o_full);
             }
         }
     } else {
@@ -146,71 +153,74 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
         float o_acc[HD];
 #pragma unroll
         for (int i = 0; i < HD; i++) o_acc[i] = 0.f;
+        uint8_t *prow = sP + (row >> 3) * 1024 + (row & 7) * 128;
 
         auto accumulate_o = [&](int j, float c) {
-            const int s = j & 1;
-            mbar_wait(&o_full[s], (j >> 1) & 1);
+            mbar_wait(&o_full, j & 1);
             tc_fence_after();
-            uint32_t r0[32], r1[32];
-            tmem_ld_32x32b_x32(tO[s] + lane_off, r0);
-            tmem_ld_32x32b_x32(tO[s] + lane_off + 32, r1);
-            tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 32; i++) {
-                o_acc[i] = o_acc[i] * c + __uint_as_float(r0[i]);
-                o_acc[32 + i] = o_acc[32 + i] * c + __uint_as_float(r1[i]);
+            for (int h2 = 0; h2 < 2; h2++) {
+                uint32_t r[32];
+                tmem_ld_32x32b_x32(tO + lane_off + h2 * 32, r);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; i++) o_acc[h2 * 32 + i] = o_acc[h2 * 32 + i] * c + __uint_as_float(r[i]);
             }
+            tc_fence_before();
+            mbar_arrive(&o_empty);
         };
 
         for (int j = 0; j < nb; j++) {
-            const int s = j & 1;
-            const uint32_t ph = (j >> 1) & 1;
-            mbar_wait(&s_full[s], ph);
+            mbar_wait(&s_full, j & 1);
             tc_fence_after();
-            float sv[AK];
-#pragma unroll
+            const int kbase = j * AK;
+            const bool ragged = kbase + AK > Nk;
+            // pass 1: row maximum (S stays in TMEM; re-reading it is cheaper than 128 live registers)
+            float mx = -INFINITY;
+#pragma unroll 1
             for (int c = 0; c < AK; c += 32) {
                 uint32_t r[32];
-                tmem_ld_32x32b_x32(tS[s] + lane_off + c, r);
+                tmem_ld_32x32b_x32(tS + lane_off + c, r);
                 tmem_ld_wait();
 #pragma unroll
-                for (int i = 0; i < 32; i++) sv[c + i] = __uint_as_float(r[i]);
-            }
-            const int kbase = j * AK;
-            float mx = -INFINITY;
-            if (kbase + AK <= Nk) {
-#pragma unroll
-                for (int i = 0; i < AK; i++) mx = fmaxf(mx, sv[i]);
-            } else {
-#pragma unroll
-                for (int i = 0; i < AK; i++) {
-                    if (kbase + i >= Nk) sv[i] = -INFINITY;
-                    mx = fmaxf(mx, sv[i]);
+                for (int i = 0; i < 32; i++) {
+                    const float v = (ragged && kbase + c + i >= Nk) ? -INFINITY : __uint_as_float(r[i]);
+                    mx = fmaxf(mx, v);
                 }
             }
             const float corr_prev = corr;
             const float m_new = fmaxf(m_run, mx * scale_log2);
-            corr = exp2f(m_run - m_new);
+            corr = ex2_fast(m_run - m_new);
             m_run = m_new;
+            // the previous block's P*V must have retired before P is overwritten; fold its result in now
+            if (j > 0) accumulate_o(j - 1, corr_prev);
+            // pass 2: p = 2^(s*scale - m), row sum, bf16 P into 128B-swizzled smem
             float lsum = 0.f;
-            uint8_t *prow = sP + s * kPBytes + (row >> 3) * 1024 + (row & 7) * 128;
+#pragma unroll 1
+            for (int c = 0; c < AK; c += 32) {
+                uint32_t r[32];
+                tmem_ld_32x32b_x32(tS + lane_off + c, r);
+                tmem_ld_wait();
+                float p[32];
 #pragma unroll
-            for (int c8 = 0; c8 < AK / 8; c8++) {
-                float p[8];
-#pragma unroll
-                for (int i = 0; i < 8; i++) {
-                    p[i] = exp2f(sv[c8 * 8 + i] * scale_log2 - m_new);
+                for (int i = 0; i < 32; i++) {
+                    const float v = (ragged && kbase + c + i >= Nk) ? -INFINITY : __uint_as_float(r[i]);
+                    p[i] = ex2_fast(fmaf(v, scale_log2, -m_new));
                     lsum += p[i];
                 }
-                const int sub = c8 >> 3, q16 = c8 & 7;
-                uint4 *dst = reinterpret_cast<uint4 *>(prow + sub * (kPBytes / 2) + ((q16 ^ (row & 7)) << 4));
-                *dst = make_uint4(pack2(p[0], p[1]), pack2(p[2], p[3]), pack2(p[4], p[5]), pack2(p[6], p[7]));
+#pragma unroll
+                for (int g = 0; g < 4; g++) {
+                    const int c8 = (c >> 3) + g;                 // 16-byte chunk index along the 128 keys
+                    const int sub = c8 >> 3, q16 = c8 & 7;
+                    uint4 *dst = reinterpret_cast<uint4 *>(prow + sub * (kPBytes / 2) + ((q16 ^ (row & 7)) << 4));
+                    *dst = make_uint4(pack2(p[8 * g], p[8 * g + 1]), pack2(p[8 * g + 2], p[8 * g + 3]),
+                                      pack2(p[8 * g + 4], p[8 * g + 5]), pack2(p[8 * g + 6], p[8 * g + 7]));
+                }
             }
             l_run = l_run * corr + lsum;
             fence_proxy_async_smem();
             tc_fence_before();
-            mbar_arrive(&p_full[s]);
-            if (j > 0) accumulate_o(j - 1, corr_prev);
+            mbar_arrive(&p_full);
         }
         accumulate_o(nb - 1, corr);
         const int q = q0 + row;
@@ -230,7 +240,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc<512>(tmem);
+        tmem_dealloc<kTmemColsAttn>(tmem);
     }
 }
 

@@ -23,7 +23,8 @@ __device__ __forceinline__ float gelu_tanh(float x)
     return 0.5f * x * (1.0f + tanhf(u));
 }
 
-// out_bf16[r, :] = RMSNorm(x[r, :]) * w  [* (1 + scale[b]) + shift[b]]      one warp per row
+// out_bf16[r, :] = RMSNorm(x[r, :]) * w  [* (1 + scale[b]) + shift[b]]      one warp per row; the row is kept in
+// registers (D <= 1024: 8 float4 per lane) so x is read once.
 __global__ void __launch_bounds__(256)
 rmsnorm_modulate_kernel(const float *__restrict__ x, const float *__restrict__ w,
                         const float *__restrict__ shift, const float *__restrict__ scale, int mod_ld,
@@ -34,8 +35,18 @@ rmsnorm_modulate_kernel(const float *__restrict__ x, const float *__restrict__ w
     if (r >= R) return;
     const float4 *xr = reinterpret_cast<const float4 *>(x + (size_t)r * D);
     const int n4 = D >> 2;
+    float4 cache[8];
     float ss = 0.f;
-    for (int i = lane; i < n4; i += 32) {
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+        const int i = lane + 32 * u;
+        if (i < n4) {
+            const float4 v = xr[i];
+            cache[u] = v;
+            ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+        }
+    }
+    for (int i = lane + 256; i < n4; i += 32) {          // D > 1024: tail re-read below
         const float4 v = xr[i];
         ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
     }
@@ -46,17 +57,23 @@ rmsnorm_modulate_kernel(const float *__restrict__ x, const float *__restrict__ w
     const float4 *sh4 = shift ? reinterpret_cast<const float4 *>(shift + (size_t)b * mod_ld) : nullptr;
     const float4 *sc4 = scale ? reinterpret_cast<const float4 *>(scale + (size_t)b * mod_ld) : nullptr;
     uint2 *o = reinterpret_cast<uint2 *>(out + (size_t)r * D);
-    for (int i = lane; i < n4; i += 32) {
-        const float4 v = xr[i], ww = w4[i];
+    auto emit = [&](int i, const float4 v) {
+        const float4 ww = __ldg(w4 + i);
         float4 y = make_float4(v.x * rs * ww.x, v.y * rs * ww.y, v.z * rs * ww.z, v.w * rs * ww.w);
         if (sc4) {
-            const float4 s = sc4[i], t = sh4[i];
+            const float4 s = __ldg(sc4 + i), t = __ldg(sh4 + i);
             y.x = y.x * (1.f + s.x) + t.x; y.y = y.y * (1.f + s.y) + t.y;
             y.z = y.z * (1.f + s.z) + t.z; y.w = y.w * (1.f + s.w) + t.w;
         }
         __nv_bfloat162 a = __floats2bfloat162_rn(y.x, y.y), c = __floats2bfloat162_rn(y.z, y.w);
         o[i] = make_uint2(*reinterpret_cast<uint32_t *>(&a), *reinterpret_cast<uint32_t *>(&c));
+    };
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+        const int i = lane + 32 * u;
+        if (i < n4) emit(i, cache[u]);
     }
+    for (int i = lane + 256; i < n4; i += 32) emit(i, xr[i]);
 }
 
 // y[b, n] = act_out( bias[n] + sum_k act_in(x[b, k]) * W[n, k] )   small batch (<= 16 rows), fp32

@@ -508,8 +508,10 @@ def DiT_L_Pixelart_clay_pcd_stage2(**kw):
 
 
 def DiT_B_Pixelart_clay_pcd_stage2(**kw):
-    return DiT_I23D_PCD_PixelArt_noclip_clay_stage2(depth=12, use_clay_ca=True, hidden_size=768, patch_size=1,
-                                                    num_heads=12, **kw)
+    # As in the reference (dit_i23d.py:1554-1559) this entry leaves num_heads at its default of 16, i.e.
+    # head_dim 48, and conditions by concatenation (use_pe_cond=False).  head_dim 48 is not supported by the
+    # B200 attention kernel, so constructing it raises ValueError; the deployed stage-2 model is the -L entry.
+    return DiT_I23D_PCD_PixelArt_noclip_clay_stage2(depth=12, use_clay_ca=True, hidden_size=768, **kw)
 
 
 DiT_models = {
