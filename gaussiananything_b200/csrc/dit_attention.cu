@@ -91,6 +91,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
     tc_fence_after();
     const uint32_t tmem = tmem_slot;
     const uint32_t tS = tmem, tO = tmem + 128;
+    pdl_wait();
+    pdl_launch_dependents();
 
     if (warp == 0) {
         if (elect_one()) {
@@ -267,7 +269,6 @@ extern "C" int ga_attention_bf16(const void *Q, const void *K, const void *Vt, v
     }
     dim3 grid((Nq + AQ - 1) / AQ, (unsigned)BH);
     const float scale_log2 = softmax_scale * 1.4426950408889634f;
-    attn_fwd_kernel<<<grid, kAttnThreads, kSmemAttn, (cudaStream_t)stream>>>(
-        tq, tk, tv, reinterpret_cast<__nv_bfloat16 *>(out), Nq, Nk, pitch_q, pitch_k, heads, scale_log2);
-    return (int)cudaGetLastError();
+    return (int)ga_launch_pdl(attn_fwd_kernel, grid, dim3(kAttnThreads), (size_t)kSmemAttn, (cudaStream_t)stream, tq, tk, tv,
+                              reinterpret_cast<__nv_bfloat16 *>(out), Nq, Nk, pitch_q, pitch_k, heads, scale_log2);
 }

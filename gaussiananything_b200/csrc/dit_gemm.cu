@@ -206,6 +206,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = tmem_slot;
+    pdl_wait();                     // inputs (A, the residual stream, the gate table) come from earlier kernels
+    pdl_launch_dependents();        // let the next kernel run its own prologue under our main loop
 
     if (warp == 0) {
         if (elect_one()) {
@@ -348,8 +350,7 @@ static int launch_gemm(const CUtensorMap &ta, const CUtensorMap &tb, const GaGem
     }
     const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
     dim3 grid(tiles < num_sms ? tiles : num_sms);
-    gemm_bf16_tn_kernel<BN><<<grid, kThreads, Cfg::kSmem, s>>>(ta, tb, ep, M, N, K);
-    return (int)cudaGetLastError();
+    return (int)ga_launch_pdl(gemm_bf16_tn_kernel<BN>, grid, dim3(kThreads), (size_t)Cfg::kSmem, s, ta, tb, ep, M, N, K);
 }
 
 extern "C" int ga_gemm_bf16_tn(const void *A, int lda, const void *W, int ldw, int M, int N, int K,

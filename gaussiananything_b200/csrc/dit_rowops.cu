@@ -7,6 +7,7 @@
 #include "../../include/ga_b200.h"
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
+#include <cstdlib>
 
 namespace {
 
@@ -32,6 +33,8 @@ rmsnorm_modulate_kernel(const float *__restrict__ x, const float *__restrict__ w
 {
     const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
+    asm volatile("griddepcontrol.wait;\n" ::: "memory");            // x comes from the previous GEMM's epilogue
+    asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
     if (r >= R) return;
     const float4 *xr = reinterpret_cast<const float4 *>(x + (size_t)r * D);
     const int n4 = D >> 2;
@@ -267,9 +270,16 @@ extern "C" int ga_rmsnorm_modulate(const float *x, const float *w, const float *
 {
     if (!x || !w || !out_bf16 || R <= 0 || D <= 0 || D % 4 || rows_per_batch <= 0) return GA_ERR_BADARG;
     if ((shift == nullptr) != (scale == nullptr)) return GA_ERR_BADARG;
-    rmsnorm_modulate_kernel<<<(R + 7) / 8, 256, 0, (cudaStream_t)stream>>>(
-        x, w, shift, scale, mod_ld, rows_per_batch, reinterpret_cast<__nv_bfloat16 *>(out_bf16), R, D, eps);
-    return last_err();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((R + 7) / 8); cfg.blockDim = dim3(256); cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    static int use_pdl = -1;
+    if (use_pdl < 0) { const char *e = getenv("GA_B200_PDL"); use_pdl = (e && e[0] == '0') ? 0 : 1; }
+    cfg.attrs = attr; cfg.numAttrs = use_pdl ? 1 : 0;
+    return (int)cudaLaunchKernelEx(&cfg, rmsnorm_modulate_kernel, x, w, shift, scale, mod_ld, rows_per_batch,
+                                   reinterpret_cast<__nv_bfloat16 *>(out_bf16), R, D, eps);
 }
 
 extern "C" int ga_linear_small(const float *x, const float *W, const float *bias, float *y, int rows, int N, int K,

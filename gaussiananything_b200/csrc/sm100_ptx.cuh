@@ -148,4 +148,32 @@ __device__ __forceinline__ void umma_commit(uint64_t *bar)
                  : "memory");
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch
+// A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start while its predecessor
+// in the stream is still running: everything before pdl_wait() (barrier init, TMEM alloc, descriptor
+// prefetch) overlaps the predecessor's tail; pdl_wait() blocks until the predecessor's memory is visible.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;\n" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory"); }
+
 }  // namespace sm100
+
+// host: launch with the PDL attribute unless GA_B200_PDL=0
+#include <cstdlib>
+template <typename... KArgs, typename... Args>
+static inline cudaError_t ga_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s,
+                                        Args... args)
+{
+    static int use_pdl = -1;
+    if (use_pdl < 0) {
+        const char *e = getenv("GA_B200_PDL");
+        use_pdl = (e && e[0] == '0') ? 0 : 1;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = use_pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
