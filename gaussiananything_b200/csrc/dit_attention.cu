@@ -51,14 +51,20 @@ __device__ __forceinline__ float ex2_fast(float x)
 // Two CTAs are co-resident per SM (97 KB smem, 256 TMEM columns, <=168 registers): while one CTA's softmax
 // warps keep the MUFU/FMA pipes busy, the other CTA's MMAs and TMA loads run -- the hardware interleaves the
 // two dependency chains, so the kernel needs no intra-CTA ping-pong.
+//
+// kStatic: the caller supplies an upper bound of |q.k| * scale (available for free when q and k are
+// RMS-normalised: |q.k| <= 64 max|w_q| max|w_k|).  exp2(s*scale - bound) then never overflows, so no running
+// maximum, no rescaling and no per-block read-out of O are needed: P*V accumulates in TMEM over all key blocks
+// and S is read from TMEM exactly once.  Mathematically identical to softmax (the constant cancels in O / l).
+template <bool kStatic>
 __global__ void __launch_bounds__(kAttnThreads, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_k,
                 const __grid_constant__ CUtensorMap tma_vt, __nv_bfloat16 *__restrict__ out,
                 const int Nq, const int Nk, const int pitch_q, const int pitch_k, const int heads,
-                const float scale_log2)
+                const float scale_log2, const float bound_log2)
 {
     extern __shared__ uint8_t smem_raw[];
-    __shared__ uint64_t q_full, k_full[2], k_empty[2], v_full, v_empty, s_full, p_full, o_full, o_empty;
+    __shared__ uint64_t q_full, k_full[2], k_empty[2], v_full, v_empty, s_full, p_full, o_full, o_empty, p_empty;
     __shared__ uint32_t tmem_slot;
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t *sQ = smem;
@@ -80,7 +86,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
             for (int s = 0; s < 2; s++) { mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1); }
             mbar_init(&v_full, 1); mbar_init(&v_empty, 1);
             mbar_init(&s_full, 1); mbar_init(&o_full, 1);
-            mbar_init(&p_full, 128); mbar_init(&o_empty, 128);
+            mbar_init(&p_full, 128); mbar_init(&o_empty, 128); mbar_init(&p_empty, 1);
             fence_barrier_init();
         }
         __syncwarp();
@@ -134,17 +140,22 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
                 mbar_wait(&p_full, ph);                 // P_j staged; S_j has been consumed
                 if (j + 1 < nb) issue_s(j + 1);         // next QK^T overlaps this block's P*V and the O read-out
                 mbar_wait(&v_full, ph);
-                mbar_wait(&o_empty, ph ^ 1);            // softmax warps have read O_{j-1}
+                if (!kStatic) mbar_wait(&o_empty, ph ^ 1);   // softmax warps have read O_{j-1}
                 tc_fence_after();
 #pragma unroll
                 for (int kk = 0; kk < AK / 16; kk++) {
                     const uint64_t sub_p = (uint64_t)((kk >> 2) * ((kPBytes / 2) >> 4));
                     const uint64_t sub_v = (uint64_t)((kk >> 2) * ((kVBytes / 2) >> 4));
                     umma_bf16_ss(tO, pd + sub_p + (uint64_t)(2 * (kk & 3)), vd + sub_v + (uint64_t)(2 * (kk & 3)),
-                                 idesc_o, kk != 0);
+                                 idesc_o, kStatic ? (uint32_t)((j | kk) != 0) : (uint32_t)(kk != 0));
                 }
                 umma_commit(&v_empty);
-                umma_commit(&o_full);
+                if (kStatic) {
+                    umma_commit(&p_empty);                  // P (and V) may be overwritten
+                    if (j == nb - 1) umma_commit(&o_full);  // O complete after the last key block
+                } else {
+                    umma_commit(&o_full);
+                }
             }
         }
     } else {
@@ -172,6 +183,52 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
             mbar_arrive(&o_empty);
         };
 
+        if (kStatic) {
+            float ls0 = 0.f, ls1 = 0.f, ls2 = 0.f, ls3 = 0.f;
+            for (int j = 0; j < nb; j++) {
+                mbar_wait(&s_full, j & 1);
+                tc_fence_after();
+                const int kbase = j * AK;
+                const bool ragged = kbase + AK > Nk;
+#pragma unroll 1
+                for (int c = 0; c < AK; c += 32) {
+                    uint32_t r[32];
+                    tmem_ld_32x32b_x32(tS + lane_off + c, r);
+                    tmem_ld_wait();
+                    float p[32];
+#pragma unroll
+                    for (int i = 0; i < 32; i++) {
+                        const float v = (ragged && kbase + c + i >= Nk) ? -INFINITY : __uint_as_float(r[i]);
+                        p[i] = ex2_fast(fmaf(v, scale_log2, -bound_log2));
+                    }
+#pragma unroll
+                    for (int i = 0; i < 32; i += 4) { ls0 += p[i]; ls1 += p[i + 1]; ls2 += p[i + 2]; ls3 += p[i + 3]; }
+                    if (c == 0 && j > 0) mbar_wait(&p_empty, (j - 1) & 1);      // P*V of the previous block retired
+#pragma unroll
+                    for (int g = 0; g < 4; g++) {
+                        const int c8 = (c >> 3) + g;
+                        const int sub = c8 >> 3, q16 = c8 & 7;
+                        uint4 *dst = reinterpret_cast<uint4 *>(prow + sub * (kPBytes / 2) + ((q16 ^ (row & 7)) << 4));
+                        *dst = make_uint4(pack2(p[8 * g], p[8 * g + 1]), pack2(p[8 * g + 2], p[8 * g + 3]),
+                                          pack2(p[8 * g + 4], p[8 * g + 5]), pack2(p[8 * g + 6], p[8 * g + 7]));
+                    }
+                }
+                fence_proxy_async_smem();
+                tc_fence_before();
+                mbar_arrive(&p_full);
+            }
+            l_run = (ls0 + ls1) + (ls2 + ls3);
+            mbar_wait(&o_full, 0);
+            tc_fence_after();
+#pragma unroll
+            for (int h2 = 0; h2 < 2; h2++) {
+                uint32_t r[32];
+                tmem_ld_32x32b_x32(tO + lane_off + h2 * 32, r);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; i++) o_acc[h2 * 32 + i] = __uint_as_float(r[i]);
+            }
+        } else {
         for (int j = 0; j < nb; j++) {
             mbar_wait(&s_full, j & 1);
             tc_fence_after();
@@ -225,6 +282,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
             mbar_arrive(&p_full);
         }
         accumulate_o(nb - 1, corr);
+        }
         const int q = q0 + row;
         if (q < Nq) {
             const float inv = 1.0f / l_run;
@@ -249,7 +307,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
 }  // namespace
 
 extern "C" int ga_attention_bf16(const void *Q, const void *K, const void *Vt, void *out, int batch, int heads,
-                                 int Nq, int Nk, int pitch_q, int pitch_k, float softmax_scale, void *stream)
+                                 int Nq, int Nk, int pitch_q, int pitch_k, float softmax_scale, float score_bound,
+                                 void *stream)
 {
     if (!Q || !K || !Vt || !out || batch <= 0 || heads <= 0 || Nq <= 0 || Nk <= 0) return GA_ERR_BADARG;
     if (pitch_q < Nq || pitch_k < Nk || pitch_k % 128 != 0) return GA_ERR_BADARG;
@@ -263,12 +322,21 @@ extern "C" int ga_attention_bf16(const void *Q, const void *K, const void *Vt, v
     if (rc) return rc;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemAttn);
+        cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemAttn);
+        if (e != cudaSuccess) return (int)e;
+        e = cudaFuncSetAttribute(attn_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemAttn);
         if (e != cudaSuccess) return (int)e;
         attr_set = true;
     }
     dim3 grid((Nq + AQ - 1) / AQ, (unsigned)BH);
-    const float scale_log2 = softmax_scale * 1.4426950408889634f;
-    return (int)ga_launch_pdl(attn_fwd_kernel, grid, dim3(kAttnThreads), (size_t)kSmemAttn, (cudaStream_t)stream, tq, tk, tv,
-                              reinterpret_cast<__nv_bfloat16 *>(out), Nq, Nk, pitch_q, pitch_k, heads, scale_log2);
+    const float log2e = 1.4426950408889634f;
+    const float scale_log2 = softmax_scale * log2e;
+    // static-bound softmax only while exp(-2*bound) stays far from the fp32/bf16 underflow range
+    const bool use_static = score_bound > 0.f && score_bound <= 40.f;
+    __nv_bfloat16 *o = reinterpret_cast<__nv_bfloat16 *>(out);
+    if (use_static)
+        return (int)ga_launch_pdl(attn_fwd_kernel<true>, grid, dim3(kAttnThreads), (size_t)kSmemAttn, (cudaStream_t)stream,
+                                  tq, tk, tv, o, Nq, Nk, pitch_q, pitch_k, heads, scale_log2, score_bound * log2e);
+    return (int)ga_launch_pdl(attn_fwd_kernel<false>, grid, dim3(kAttnThreads), (size_t)kSmemAttn, (cudaStream_t)stream,
+                              tq, tk, tv, o, Nq, Nk, pitch_q, pitch_k, heads, scale_log2, 0.0f);
 }

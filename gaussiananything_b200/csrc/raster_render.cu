@@ -129,6 +129,7 @@ render_fwd_kernel(RasterDims d, RasterWs ws, const float *__restrict__ bg,
         __syncthreads();
         for (int g0 = 0; g0 < cnt; g0 += 32) {
             if (__all_sync(0xffffffffu, done)) break;
+            // level 1: which of these 32 surfels can touch this warp's 8x4 block at all
             const int j = g0 + lane;
             bool hit = false;
             if (j < cnt) {
@@ -136,9 +137,21 @@ render_fwd_kernel(RasterDims d, RasterWs ws, const float *__restrict__ bg,
                 hit = !(bb.y < bx_lo || bb.x > bx_hi || bb.w < by_lo || bb.z > by_hi);
             }
             unsigned mask = __ballot_sync(0xffffffffu, hit);
+            // level 2: per-lane stream = the hits whose cull box contains THIS pixel.  Each lane then walks its
+            // own stream (in list order, so compositing order is unchanged); lanes evaluate different surfels
+            // in the same instruction, which roughly halves the number of evaluation rounds.
+            unsigned mine = 0;
             while (mask) {
-                const int jj = g0 + __ffs(mask) - 1;
+                const int b = __ffs(mask) - 1;
                 mask &= mask - 1;
+                const float4 bb = s_rec[4][g0 + b];
+                if (dxf >= bb.x && dxf <= bb.y && dyf >= bb.z && dyf <= bb.w) mine |= 1u << b;
+            }
+            if (done) mine = 0;
+            while (__any_sync(0xffffffffu, mine != 0)) {
+                const bool active = mine != 0;
+                const int jj = g0 + (active ? __ffs(mine) - 1 : 0);
+                mine &= mine - 1;
                 const float4 f0 = s_rec[0][jj], f1 = s_rec[1][jj], f2 = s_rec[2][jj], f3 = s_rec[3][jj];
                 const float p0 = f0.x + dxf * f0.w + dyf * f1.z;
                 const float p1 = f0.y + dxf * f1.x + dyf * f1.w;
@@ -152,15 +165,14 @@ render_fwd_kernel(RasterDims d, RasterWs ws, const float *__restrict__ bg,
                 const float depth = (rho3d <= rho2d) ? (s0 * f2.y + s1 * f2.z) + f2.w : f2.w;
                 // power = -0.5*rho > 0 never happens for rho >= 0; NaN rho (p2 == 0) fails the alpha test
                 const float alpha = fminf(0.99f, f3.z * fast_ex2(rho * GA_NEG_HALF_LOG2E));
-                bool ok = !done && p2 != 0.0f && depth >= GA_NEAR_N && alpha >= 1.0f / 255.0f;
-                float test_T = 0.f;
+                bool ok = active && p2 != 0.0f && depth >= GA_NEAR_N && alpha >= 1.0f / 255.0f;
                 if (ok) {
-                    test_T = T * (1 - alpha);
-                    if (test_T < 0.0001f) { done = true; ok = false; }
-                }
-                if (__any_sync(0xffffffffu, ok)) {
-                    const float4 nr = s_rec[5][jj], gb = s_rec[6][jj];
-                    if (ok) {
+                    const float test_T = T * (1 - alpha);
+                    if (test_T < 0.0001f) {
+                        done = true;
+                        mine = 0;
+                    } else {
+                        const float4 nr = s_rec[5][jj], gb = s_rec[6][jj];
                         const int contributor = c0 + jj + 1;
                         const float w = alpha * T;
                         const float A = 1 - T;
@@ -208,35 +220,175 @@ cudaError_t ga_launch_render_fwd(const RasterDims &d, const RasterWs &w, const f
 
 // ---------------------------------------------------------------------------
 // K4 backward
+//
+// Two phases per group of G staged surfels (G = 32, 16 or 8, picked per chunk so that a surfel's cull box
+// clipped to the tile never holds more pixels than its list capacity 2048/G):
+//   phase A (pixel-parallel, back to front): every lane walks its own stream of surfels whose cull box
+//     contains its pixel, recomputes alpha, runs the compositing recurrences and appends a 16-byte record
+//     (pixel, dL/dalpha, dL/dz, w) to the surfel's list in shared memory;
+//   phase B (surfel-parallel): 256/G threads share a surfel, re-derive the ray-splat geometry of each
+//     recorded pixel, accumulate the 18 gradient components in registers and reduce-scatter them over the
+//     256/G lanes; one global atomic per (tile, surfel, component).
+// This replaces a 32-lane reduction per (warp, surfel) hit -- where typically 8 of 32 lanes carried data --
+// by register accumulation over the pixels a surfel actually touches.
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ float warp_sum(float v)
+#define BWD_LIST_RECORDS 2048
+
+struct BwdSmem {
+    float4 rec[6][CHUNK];
+    uint4 list[BWD_LIST_RECORDS];
+    float up[256][6];               // per pixel: dL/dcolor (3), dL/dnormal (3)
+    uint32_t id[CHUNK];
+    int cnt[2][32];
+    int maxc;
+};
+
+// reduce-scatter of 18 components over TPI (8/16/32) consecutive lanes by recursive halving
+template <int TPI>
+__device__ __forceinline__ void reduce_scatter18(const float (&g)[GA_GRAD_F], int lane, float *__restrict__ dst)
 {
+    int off = 0, size = 18;
+    float a9[10];
+    {
+        const bool u = lane & (TPI >> 1);
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
+        for (int i = 0; i < 9; i++) {
+            const float keep = u ? g[9 + i] : g[i], send = u ? g[i] : g[9 + i];
+            a9[i] = keep + __shfl_xor_sync(0xffffffffu, send, TPI >> 1);
+        }
+        a9[9] = 0.f;
+        off += u ? 9 : 0; size = 9;
+    }
+    float b5[6];
+    {
+        const bool u = lane & (TPI >> 2);
+#pragma unroll
+        for (int i = 0; i < 5; i++) {
+            const float keep = u ? a9[5 + i] : a9[i], send = u ? a9[i] : a9[5 + i];
+            b5[i] = keep + __shfl_xor_sync(0xffffffffu, send, TPI >> 2);
+        }
+        b5[5] = 0.f;
+        off += u ? 5 : 0; size = u ? 4 : 5;
+    }
+    float c3[4];
+    {
+        const bool u = lane & (TPI >> 3);
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+            const float keep = u ? b5[3 + i] : b5[i], send = u ? b5[i] : b5[3 + i];
+            c3[i] = keep + __shfl_xor_sync(0xffffffffu, send, TPI >> 3);
+        }
+        c3[3] = 0.f;
+        off += u ? 3 : 0; size = u ? size - 3 : 3;
+    }
+    if constexpr (TPI == 8) {
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+            if (i < size && c3[i] != 0.f) atomicAdd(dst + off + i, c3[i]);
+        return;
+    } else {
+        float d2[2];
+        {
+            const bool u = lane & (TPI >> 4);
+#pragma unroll
+            for (int i = 0; i < 2; i++) {
+                const float keep = u ? c3[2 + i] : c3[i], send = u ? c3[i] : c3[2 + i];
+                d2[i] = keep + __shfl_xor_sync(0xffffffffu, send, TPI >> 4);
+            }
+            off += u ? 2 : 0; size = u ? max(size - 2, 0) : min(size, 2);
+        }
+        if constexpr (TPI == 16) {
+#pragma unroll
+            for (int i = 0; i < 2; i++)
+                if (i < size && d2[i] != 0.f) atomicAdd(dst + off + i, d2[i]);
+            return;
+        } else {
+            const bool u = lane & 1;
+            const float keep = u ? d2[1] : d2[0], send = u ? d2[0] : d2[1];
+            const float e = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+            off += u ? 1 : 0; size = u ? max(size - 1, 0) : min(size, 1);
+            if (size > 0 && e != 0.f) atomicAdd(dst + off, e);
+        }
+    }
 }
 
-__global__ void __launch_bounds__(256)
+template <int TPI>
+__device__ __forceinline__ void bwd_phase_b(BwdSmem &sm, const int *cnt, int g0, int gcnt, int cap, int ox, int oy,
+                                            float *__restrict__ acc_base)
+{
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int inst = tid / TPI, sub = tid % TPI;
+    const bool valid = inst < gcnt;
+    const int n = valid ? min(cnt[inst], cap) : 0;
+    float g[GA_GRAD_F];
+#pragma unroll
+    for (int f = 0; f < GA_GRAD_F; f++) g[f] = 0.f;
+    if (n > 0) {
+        const int jj = g0 + inst;
+        const float4 a = sm.rec[0][jj], b = sm.rec[1][jj], c = sm.rec[2][jj];
+        const float opa = c.w;
+        for (int r = sub; r < n; r += TPI) {
+            const uint4 rc = sm.list[inst * cap + r];
+            const int pix = (int)rc.x;
+            const float dL_dalpha = __uint_as_float(rc.y), dL_dz = __uint_as_float(rc.z), w = __uint_as_float(rc.w);
+            const float pfx = (float)(ox + (pix & 15)), pfy = (float)(oy + (pix >> 4));
+            PixelGeom pg;
+            float k0, k1, k2, l0, l1, l2;
+            eval_pair(a, b, c, pfx, pfy, pg, k0, k1, k2, l0, l1, l2);      // same code path as phase A: same bits
+            const float G = pg.G;
+            const float dL_dG = opa * dL_dalpha;                           // 0.99 clamp passed through (upstream)
+            if (pg.use3d) {
+                const float dL_ds0 = dL_dG * -G * pg.s0 + dL_dz * b.z;
+                const float dL_ds1 = dL_dG * -G * pg.s1 + dL_dz * b.w;
+                const float ip = fast_rcp(pg.p2);
+                const float q0 = dL_ds0 * ip, q1 = dL_ds1 * ip;
+                const float q2 = -(q0 * pg.s0 + q1 * pg.s1);
+                const float dk0 = l1 * q2 - l2 * q1, dk1 = l2 * q0 - l0 * q2, dk2 = l0 * q1 - l1 * q0;
+                const float dl0 = q1 * k2 - q2 * k1, dl1 = q2 * k0 - q0 * k2, dl2 = q0 * k1 - q1 * k0;
+                g[0] -= dk0; g[1] -= dk1; g[2] -= dk2;
+                g[3] -= dl0; g[4] -= dl1; g[5] -= dl2;
+                g[6] += pfx * dk0 + pfy * dl0 + dL_dz * pg.s0;
+                g[7] += pfx * dk1 + pfy * dl1 + dL_dz * pg.s1;
+                g[8] += pfx * dk2 + pfy * dl2 + dL_dz;
+            } else {
+                g[9] += dL_dG * (-G * GA_FILTER_INV_SQUARE * pg.dx);
+                g[10] += dL_dG * (-G * GA_FILTER_INV_SQUARE * pg.dy);
+                g[8] += dL_dz;
+            }
+            g[14] += G * dL_dalpha;
+            const float *up = sm.up[pix];
+            g[15] += w * up[0]; g[16] += w * up[1]; g[17] += w * up[2];
+            g[11] += w * up[3]; g[12] += w * up[4]; g[13] += w * up[5];
+        }
+    }
+    // all lanes of the warp take part in the shuffles; groups whose surfel recorded nothing carry zeros
+    const int any = __any_sync(0xffffffffu, n > 0);
+    if (any) {
+        float *dst = acc_base + (size_t)(valid ? sm.id[g0 + inst] : 0) * GA_GRAD_F;
+        reduce_scatter18<TPI>(g, lane, dst);
+    }
+}
+
+__global__ void __launch_bounds__(256, 3)
 render_bwd_kernel(RasterDims d, RasterWs ws, const float *__restrict__ bg,
                   const float *__restrict__ dL_dcolor, const float *__restrict__ dL_dallmap,
                   float *__restrict__ grad_acc)
 {
-    __shared__ float4 s_rec[6][CHUNK];
-    __shared__ float s_acc[CHUNK][GA_GRAD_F + 1];
-    __shared__ uint32_t s_id[CHUNK];
-    __shared__ int s_touched[CHUNK];
-    __shared__ int s_maxc;
+    extern __shared__ __align__(16) uint8_t bwd_smem_raw[];
+    BwdSmem &sm = *reinterpret_cast<BwdSmem *>(bwd_smem_raw);
     if (ws.status[1]) return;
     const int view = blockIdx.z;
     const int tile = blockIdx.y * d.gx + blockIdx.x;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int wx0 = blockIdx.x * GA_BLOCK_X + (warp & 1) * 8;
-    const int wy0 = blockIdx.y * GA_BLOCK_Y + (warp >> 1) * 4;
-    const int pxi = wx0 + (lane & 7), pyi = wy0 + (lane >> 3);
+    const int ox = blockIdx.x * GA_BLOCK_X, oy = blockIdx.y * GA_BLOCK_Y;
+    const int lx0 = (warp & 1) * 8, ly0 = (warp >> 1) * 4;
+    const int lxi = lx0 + (lane & 7), lyi = ly0 + (lane >> 3);
+    const int pxi = ox + lxi, pyi = oy + lyi;
+    const int pix_local = lyi * 16 + lxi;
     const bool inside = pxi < d.W && pyi < d.H;
     const float pfx = (float)pxi, pfy = (float)pyi;
-    const float bx_lo = (float)wx0, bx_hi = (float)(wx0 + 7);
-    const float by_lo = (float)wy0, by_hi = (float)(wy0 + 3);
+    const float bx_lo = (float)(ox + lx0), bx_hi = (float)(ox + lx0 + 7);
+    const float by_lo = (float)(oy + ly0), by_hi = (float)(oy + ly0 + 3);
 
     const uint32_t start = ws.tile_start[(size_t)view * d.T + tile];
     const size_t HW = (size_t)d.H * d.W;
@@ -260,6 +412,10 @@ render_bwd_kernel(RasterDims d, RasterWs ws, const float *__restrict__ bg,
         dn0 = ga[pix + 2 * HW]; dn1 = ga[pix + 3 * HW]; dn2 = ga[pix + 4 * HW];
         dL_dmedian = ga[pix + 5 * HW]; dL_dreg = ga[pix + 6 * HW];
     }
+    {
+        float *up = sm.up[pix_local];
+        up[0] = dpx0; up[1] = dpx1; up[2] = dpx2; up[3] = dn0; up[4] = dn1; up[5] = dn2;
+    }
     const float final_D = inside ? fT[pix + HW] : 0.f, final_D2 = inside ? fT[pix + 2 * HW] : 0.f;
     const float final_A = 1 - T_final;
     const float bg_dot_dpixel = bg[0] * dpx0 + bg[1] * dpx1 + bg[2] * dpx2;
@@ -268,56 +424,75 @@ render_bwd_kernel(RasterDims d, RasterWs ws, const float *__restrict__ bg,
     float accum_depth_rec = 0, accum_alpha_rec = 0, an0 = 0, an1 = 0, an2 = 0, last_dL_dT = 0;
 
     // nothing behind the deepest contributor of the tile can receive gradient
-    if (threadIdx.x == 0) s_maxc = 0;
+    if (threadIdx.x == 0) sm.maxc = 0;
+    if (threadIdx.x < 64) sm.cnt[threadIdx.x >> 5][threadIdx.x & 31] = 0;
     __syncthreads();
     {
         int m = last_contributor;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
-        if (lane == 0) atomicMax(&s_maxc, m);
+        if (lane == 0) atomicMax(&sm.maxc, m);
     }
     __syncthreads();
-    const int total = s_maxc;          // list positions [0,total) matter
+    const int total = sm.maxc;          // list positions [0,total) matter
+    int parity = 0;
 
     for (int hi = total; hi > 0; hi -= CHUNK) {
         const int lo = max(0, hi - CHUNK);
         const int cnt = hi - lo;
         // stage positions lo..hi-1; slot t holds position hi-1-t (back to front)
+        int big64 = 0, big128 = 0;
         if ((int)threadIdx.x < cnt) {
             const uint32_t id = ws.ids[start + (hi - 1 - threadIdx.x)];
-            s_id[threadIdx.x] = id;
+            sm.id[threadIdx.x] = id;
             const float4 *src = reinterpret_cast<const float4 *>(rec_base + (size_t)id * GA_REC_F);
+            float4 q[6];
 #pragma unroll
-            for (int q = 0; q < 6; q++) s_rec[q][threadIdx.x] = __ldg(src + q);
-#pragma unroll
-            for (int f = 0; f < GA_GRAD_F; f++) s_acc[threadIdx.x][f] = 0.f;
-            s_touched[threadIdx.x] = 0;
+            for (int k = 0; k < 6; k++) { q[k] = __ldg(src + k); sm.rec[k][threadIdx.x] = q[k]; }
+            // pixels of this tile inside the cull box (upper bound of the surfel's list length)
+            const float x0 = fmaxf(q[4].x, (float)ox), x1 = fminf(q[4].y, (float)(ox + 15));
+            const float y0 = fmaxf(q[4].z, (float)oy), y1 = fminf(q[4].w, (float)(oy + 15));
+            const int wx = max(0, (int)floorf(x1) - (int)ceilf(x0) + 1), wy = max(0, (int)floorf(y1) - (int)ceilf(y0) + 1);
+            const int area = wx * wy;
+            big64 = area > 64; big128 = area > 128;
         }
-        __syncthreads();
-        for (int g0 = 0; g0 < cnt; g0 += 32) {
-            const int j = g0 + lane;
+        const int any64 = __syncthreads_or(big64);
+        const int any128 = __syncthreads_or(big128);
+        const int G = any128 ? 8 : (any64 ? 16 : 32);
+        const int cap = BWD_LIST_RECORDS / G;
+
+        for (int g0 = 0; g0 < cnt; g0 += G, parity ^= 1) {
+            const int gcnt = min(G, cnt - g0);
+            int *cntp = sm.cnt[parity];
+            // ---------------- phase A
             bool hit = false;
-            if (j < cnt) {
-                const float4 bb = s_rec[4][j];
+            if (lane < gcnt) {
+                const float4 bb = sm.rec[4][g0 + lane];
                 hit = !(bb.y < bx_lo || bb.x > bx_hi || bb.w < by_lo || bb.z > by_hi);
             }
             unsigned mask = __ballot_sync(0xffffffffu, hit);
+            unsigned mine = 0;
             while (mask) {
-                const int jj = g0 + __ffs(mask) - 1;
+                const int b = __ffs(mask) - 1;
                 mask &= mask - 1;
+                const float4 bb = sm.rec[4][g0 + b];
+                if (pfx >= bb.x && pfx <= bb.y && pfy >= bb.z && pfy <= bb.w && (hi - 1 - (g0 + b)) < last_contributor)
+                    mine |= 1u << b;
+            }
+            if (!inside) mine = 0;
+            while (__any_sync(0xffffffffu, mine != 0)) {
+                const bool active = mine != 0;
+                const int bsel = active ? __ffs(mine) - 1 : 0;
+                mine &= mine - 1;
+                const int jj = g0 + bsel;
                 const int contributor = hi - 1 - jj;       // 0-based list position
-                const float4 a = s_rec[0][jj], b = s_rec[1][jj], c = s_rec[2][jj];
+                const float4 a = sm.rec[0][jj], b = sm.rec[1][jj], c = sm.rec[2][jj];
                 PixelGeom pg;
                 float k0, k1, k2, l0, l1, l2;
-                const bool ok = inside && contributor < last_contributor &&
-                                eval_pair(a, b, c, pfx, pfy, pg, k0, k1, k2, l0, l1, l2);
-                if (!__any_sync(0xffffffffu, ok)) continue;
-                float g[GA_GRAD_F];
-#pragma unroll
-                for (int f = 0; f < GA_GRAD_F; f++) g[f] = 0.f;
+                const bool ok = active && eval_pair(a, b, c, pfx, pfy, pg, k0, k1, k2, l0, l1, l2);
                 if (ok) {
-                    const float4 nr = s_rec[3][jj], gb = s_rec[5][jj];
-                    const float alpha = pg.alpha, G = pg.G, c_d = pg.depth, opa = c.w;
+                    const float4 nr = sm.rec[3][jj], gb = sm.rec[5][jj];
+                    const float alpha = pg.alpha, c_d = pg.depth;
                     const float inv1ma = fast_rcp(1.f - alpha);
                     T = T * inv1ma;
                     const float w = alpha * T;
@@ -326,7 +501,6 @@ render_bwd_kernel(RasterDims d, RasterWs ws, const float *__restrict__ bg,
                     ar1 = last_alpha * lc1 + (1.f - last_alpha) * ar1; lc1 = gb.x;
                     ar2 = last_alpha * lc2 + (1.f - last_alpha) * ar2; lc2 = gb.y;
                     dL_dalpha += (nr.w - ar0) * dpx0 + (gb.x - ar1) * dpx1 + (gb.y - ar2) * dpx2;
-                    g[15] = w * dpx0; g[16] = w * dpx1; g[17] = w * dpx2;
                     float dL_dz = 0.0f;
                     const float inv_cd = fast_rcp(c_d);
                     const float m_d = GA_M_C0 - GA_M_C1 * inv_cd;
@@ -346,86 +520,24 @@ render_bwd_kernel(RasterDims d, RasterWs ws, const float *__restrict__ bg,
                     an1 = last_alpha * ln1 + (1.f - last_alpha) * an1; ln1 = nr.y;
                     an2 = last_alpha * ln2 + (1.f - last_alpha) * an2; ln2 = nr.z;
                     dL_dalpha += (nr.x - an0) * dn0 + (nr.y - an1) * dn1 + (nr.z - an2) * dn2;
-                    g[11] = w * dn0; g[12] = w * dn1; g[13] = w * dn2;
                     dL_dalpha *= T;
                     last_alpha = alpha;
                     dL_dalpha += (-T_final * inv1ma) * bg_dot_dpixel;
-                    const float dL_dG = opa * dL_dalpha;       // clamp passed through (upstream)
                     dL_dz += w * dL_ddepth;
-                    if (pg.use3d) {
-                        const float Tw0 = b.z, Tw1 = b.w;
-                        const float dL_ds0 = dL_dG * -G * pg.s0 + dL_dz * Tw0;
-                        const float dL_ds1 = dL_dG * -G * pg.s1 + dL_dz * Tw1;
-                        const float ip = fast_rcp(pg.p2);
-                        const float q0 = dL_ds0 * ip, q1 = dL_ds1 * ip;
-                        const float q2 = -(q0 * pg.s0 + q1 * pg.s1);
-                        const float dk0 = l1 * q2 - l2 * q1, dk1 = l2 * q0 - l0 * q2, dk2 = l0 * q1 - l1 * q0;
-                        const float dl0 = q1 * k2 - q2 * k1, dl1 = q2 * k0 - q0 * k2, dl2 = q0 * k1 - q1 * k0;
-                        g[0] = -dk0; g[1] = -dk1; g[2] = -dk2;
-                        g[3] = -dl0; g[4] = -dl1; g[5] = -dl2;
-                        g[6] = pfx * dk0 + pfy * dl0 + dL_dz * pg.s0;
-                        g[7] = pfx * dk1 + pfy * dl1 + dL_dz * pg.s1;
-                        g[8] = pfx * dk2 + pfy * dl2 + dL_dz;
-                    } else {
-                        g[9] = dL_dG * (-G * GA_FILTER_INV_SQUARE * pg.dx);
-                        g[10] = dL_dG * (-G * GA_FILTER_INV_SQUARE * pg.dy);
-                        g[8] = dL_dz;
-                    }
-                    g[14] = G * dL_dalpha;
+                    const int slot = atomicAdd(&cntp[bsel], 1);
+                    if (slot < cap)
+                        sm.list[bsel * cap + slot] = make_uint4((uint32_t)pix_local, __float_as_uint(dL_dalpha),
+                                                                __float_as_uint(dL_dz), __float_as_uint(w));
                 }
-                // recursive-halving reduction of the 18 components over 32 lanes in
-                // 9+5+3+2+1 = 20 exchanges (a butterfly per component would take 90):
-                // each level halves the component set a lane is responsible for.
-                {
-                    const bool u4 = lane & 16, u3 = lane & 8, u2 = lane & 4, u1 = lane & 2, u0 = lane & 1;
-                    float a9[10];
-#pragma unroll
-                    for (int i = 0; i < 9; i++) {
-                        const float keep = u4 ? g[9 + i] : g[i], send = u4 ? g[i] : g[9 + i];
-                        a9[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-                    }
-                    a9[9] = 0.f;
-                    float b5[6];
-#pragma unroll
-                    for (int i = 0; i < 5; i++) {
-                        const float keep = u3 ? a9[5 + i] : a9[i], send = u3 ? a9[i] : a9[5 + i];
-                        b5[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-                    }
-                    b5[5] = 0.f;
-                    float c3[4];
-#pragma unroll
-                    for (int i = 0; i < 3; i++) {
-                        const float keep = u2 ? b5[3 + i] : b5[i], send = u2 ? b5[i] : b5[3 + i];
-                        c3[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-                    }
-                    c3[3] = 0.f;
-                    float d2[2];
-#pragma unroll
-                    for (int i = 0; i < 2; i++) {
-                        const float keep = u1 ? c3[2 + i] : c3[i], send = u1 ? c3[i] : c3[2 + i];
-                        d2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-                    }
-                    const float keep = u0 ? d2[1] : d2[0], send = u0 ? d2[0] : d2[1];
-                    const float tot = keep + __shfl_xor_sync(0xffffffffu, send, 1);
-                    const int i4 = (u0 ? 1 : 0) + (u1 ? 2 : 0);          // index inside the 3-group
-                    const int i3 = i4 + (u2 ? 3 : 0);                    // inside the 5-group
-                    const int i2 = i3 + (u3 ? 5 : 0);                    // inside the 9-group
-                    const int comp = i2 + (u4 ? 9 : 0);
-                    if (i4 < 3 && i3 < 5 && i2 < 9) atomicAdd(&s_acc[jj][comp], tot);
-                }
-                if (lane == 0) s_touched[jj] = 1;
             }
+            __syncthreads();
+            // ---------------- phase B
+            if (threadIdx.x < 32) sm.cnt[parity ^ 1][threadIdx.x] = 0;      // counters of the next group
+            if (G == 32) bwd_phase_b<8>(sm, cntp, g0, gcnt, cap, ox, oy, acc_base);
+            else if (G == 16) bwd_phase_b<16>(sm, cntp, g0, gcnt, cap, ox, oy, acc_base);
+            else bwd_phase_b<32>(sm, cntp, g0, gcnt, cap, ox, oy, acc_base);
+            __syncthreads();
         }
-        __syncthreads();
-        if ((int)threadIdx.x < cnt && s_touched[threadIdx.x]) {
-            float *dst = acc_base + (size_t)s_id[threadIdx.x] * GA_GRAD_F;
-#pragma unroll
-            for (int f = 0; f < GA_GRAD_F; f++) {
-                const float v = s_acc[threadIdx.x][f];
-                if (v != 0.f) atomicAdd(dst + f, v);
-            }
-        }
-        __syncthreads();
     }
 }
 
@@ -433,7 +545,14 @@ cudaError_t ga_launch_render_bwd(const RasterDims &d, const RasterWs &w, const f
                                  const float *dL_dcolor, const float *dL_dallmap,
                                  float *grad_acc, cudaStream_t s)
 {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(render_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)sizeof(BwdSmem));
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
     dim3 grid(d.gx, d.gy, d.NV);
-    render_bwd_kernel<<<grid, 256, 0, s>>>(d, w, bg, dL_dcolor, dL_dallmap, grad_acc);
+    render_bwd_kernel<<<grid, 256, sizeof(BwdSmem), s>>>(d, w, bg, dL_dcolor, dL_dallmap, grad_acc);
     return cudaGetLastError();
 }

@@ -48,7 +48,7 @@ def _bind():
         return L
     vp, i32, i64, f32 = C.c_void_p, C.c_int, C.c_int64, C.c_float
     L.ga_gemm_bf16_tn.argtypes = [vp, i32, vp, i32, i32, i32, i32, C.POINTER(GaGemmEpilogue), i32, vp]
-    L.ga_attention_bf16.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, f32, vp]
+    L.ga_attention_bf16.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, f32, f32, vp]
     L.ga_rmsnorm_modulate.argtypes = [vp, vp, vp, vp, i32, i32, vp, i32, i32, f32, vp]
     L.ga_linear_small.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]
     L.ga_timestep_sinusoid.argtypes = [vp, vp, i32, i32, vp]
@@ -333,7 +333,11 @@ class _DiTEngine:
                 cao_w=b16(ca.to_out[0].weight), cao_b=f32(ca.to_out[0].bias),
                 qkv_w=b16(sa.qkv.weight), qkv_b=f32(sa.qkv.bias), q_n=f32(sa.q_norm.weight), k_n=f32(sa.k_norm.weight),
                 proj_w=b16(sa.proj.weight), proj_b=f32(sa.proj.bias),
-                w1=b16(mlp[0].weight), b1=f32(mlp[1].bias), w2=b16(mlp[2].weight), b2=f32(mlp[3].bias)))
+                w1=b16(mlp[0].weight), b1=f32(mlp[1].bias), w2=b16(mlp[2].weight), b2=f32(mlp[3].bias),
+                # |q.k|/8 <= (sqrt(64) max|wq|)(sqrt(64) max|wk|)/8 for RMS-normalised q, k (+2% for bf16 rounding):
+                # lets the attention kernel skip the running maximum (ga_b200.h: score_bound)
+                ca_bound=8.16 * float(ca.q_norm.weight.abs().max()) * float(ca.k_norm.weight.abs().max()),
+                sa_bound=8.16 * float(sa.q_norm.weight.abs().max()) * float(sa.k_norm.weight.abs().max())))
         self.w, self.wb = w, blocks
 
     # ---- workspaces for a (B, N, M) problem
@@ -416,7 +420,7 @@ class _DiTEngine:
                        self._epi(EPI_HEADS, q=s["q"], qn_w=wb["caq_n"], heads=H, first_part=0, tok_pitch=self.Np,
                                  rows_per_batch=N), st)
             _ck(L.ga_attention_bf16(_p(s["q"]), _p(s["kc"][l]), _p(s["vtc"][l]), _p(s["ao"]), B, H, N, M, self.Np,
-                                    self.Mp, scale, st), "cross attention")
+                                    self.Mp, scale, wb["ca_bound"], st), "cross attention")
             self._gemm(s["ao"], wb["cao_w"], R, D, D,
                        self._epi(EPI_RESID_GATE_F32, bias=wb["cao_b"], out=s["xres"], ld_out=D, rows_per_batch=N), st)
             # gated self attention
@@ -426,7 +430,7 @@ class _DiTEngine:
                        self._epi(EPI_HEADS, bias=wb["qkv_b"], q=s["q"], k=s["k"], vt=s["vt"], qn_w=wb["q_n"],
                                  kn_w=wb["k_n"], heads=H, first_part=0, tok_pitch=self.Np, rows_per_batch=N), st)
             _ck(L.ga_attention_bf16(_p(s["q"]), _p(s["k"]), _p(s["vt"]), _p(s["ao"]), B, H, N, N, self.Np, self.Np,
-                                    scale, st), "self attention")
+                                    scale, wb["sa_bound"], st), "self attention")
             self._gemm(s["ao"], wb["proj_w"], R, D, D,
                        self._epi(EPI_RESID_GATE_F32, bias=wb["proj_b"], out=s["xres"], ld_out=D, gate=ch(2),
                                  gate_ld=6 * D, rows_per_batch=N), st)

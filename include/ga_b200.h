@@ -140,7 +140,11 @@ int ga_gemm_bf16_tn(const void *A, int lda, const void *W, int ldw, int M, int N
  * Vt [B*H, 64, pitch_k] (bf16, padding beyond Nk must be finite); out [B, Nq, H*64] bf16.
  * pitch_k must be a multiple of 128. */
 int ga_attention_bf16(const void *Q, const void *K, const void *Vt, void *out, int batch, int heads,
-                      int Nq, int Nk, int pitch_q, int pitch_k, float softmax_scale, void *stream);
+                      int Nq, int Nk, int pitch_q, int pitch_k, float softmax_scale, float score_bound,
+                      void *stream);
+/* score_bound: an upper bound of |q.k| * softmax_scale over all (q, k) pairs, or <= 0 if unknown.  With
+ * RMS-normalised q and k (the DiT's qk-norm) it is 64 * max|w_q| * max|w_k| * softmax_scale; when given
+ * (and <= 40) the kernel uses it instead of a running row maximum (same result, one pass over the scores). */
 
 /* out_bf16[r,:] = RMSNorm(x[r,:]; eps) * w [* (1 + scale[b,:]) + shift[b,:]], b = r / rows_per_batch;
  * shift/scale both NULL or both set, rows mod_ld apart. */

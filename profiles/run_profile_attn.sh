@@ -11,7 +11,7 @@ B, H, N = 2, 12, 2048
 q = torch.randn(B*H, N, 64, device=dev).bfloat16(); k = torch.randn(B*H, N, 64, device=dev).bfloat16()
 vt = torch.randn(B*H, 64, N, device=dev).bfloat16(); o = torch.zeros(B, N, H*64, device=dev, dtype=torch.bfloat16)
 for _ in range(4):
-    L.ga_attention_bf16(dit._p(q), dit._p(k), dit._p(vt), dit._p(o), B, H, N, N, N, N, 0.125, st)
+    L.ga_attention_bf16(dit._p(q), dit._p(k), dit._p(vt), dit._p(o), B, H, N, N, N, N, 0.125, 20.0, st)
 torch.cuda.synchronize()
 PY
 ncu --set full --clock-control none --import-source on -k regex:attn_fwd -s 2 -c 1 -o gpurun_out/prof_attn \

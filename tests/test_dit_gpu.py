@@ -97,19 +97,24 @@ def test_gemm_epilogues():
     assert float(q.view(B, H, Np, 64)[:, :, Ntok:].abs().max()) == 0.0          # padding untouched
 
 
+@pytest.mark.parametrize("static_bound", [False, True])
 @pytest.mark.parametrize("B,H,Nq,Nk", [(1, 1, 128, 128), (2, 3, 200, 1369), (1, 2, 768, 768), (2, 12, 2048, 2048)])
-def test_attention(B, H, Nq, Nk):
+def test_attention(B, H, Nq, Nk, static_bound):
     dit, L, dev, st = _env()
     torch.manual_seed(Nq + Nk)
     pq, pk = (Nq + 127) // 128 * 128, (Nk + 127) // 128 * 128
     q = torch.zeros(B * H, pq, 64, device=dev, dtype=torch.bfloat16)
     k = torch.zeros(B * H, pk, 64, device=dev, dtype=torch.bfloat16)
     vt = torch.zeros(B * H, 64, pk, device=dev, dtype=torch.bfloat16)
-    q[:, :Nq] = torch.randn(B * H, Nq, 64, device=dev) * 1.5
-    k[:, :Nk] = torch.randn(B * H, Nk, 64, device=dev) * 1.5
+    q[:, :Nq] = torch.randn(B * H, Nq, 64, device=dev) * 1.2
+    k[:, :Nk] = torch.randn(B * H, Nk, 64, device=dev) * 1.2
     vt[:, :, :Nk] = torch.randn(B * H, 64, Nk, device=dev)
     out = torch.zeros(B, Nq, H * 64, device=dev, dtype=torch.bfloat16)
-    rc = L.ga_attention_bf16(dit._p(q), dit._p(k), dit._p(vt), dit._p(out), B, H, Nq, Nk, pq, pk, 0.125, st)
+    # static mode: a valid upper bound of |q.k|/8 (here Cauchy-Schwarz on the actual norms); 0 = online softmax
+    bound = float(q.float().norm(dim=-1).max() * k.float().norm(dim=-1).max()) / 8.0 if static_bound else 0.0
+    if static_bound:
+        assert bound <= 40.0
+    rc = L.ga_attention_bf16(dit._p(q), dit._p(k), dit._p(vt), dit._p(out), B, H, Nq, Nk, pq, pk, 0.125, bound, st)
     assert rc == 0, rc
     torch.cuda.synchronize()
     ref = torch.nn.functional.scaled_dot_product_attention(

@@ -53,7 +53,7 @@ def attn_case(B, H, Nq, Nk):
     k[:, :Nk] = torch.randn(B * H, Nk, 64, device=dev)
     vt[:, :, :Nk] = torch.randn(B * H, 64, Nk, device=dev)
     out = torch.zeros(B, Nq, H * 64, device=dev, dtype=torch.bfloat16)
-    rc = L.ga_attention_bf16(dit._p(q), dit._p(k), dit._p(vt), dit._p(out), B, H, Nq, Nk, pq, pk, 0.125, st)
+    rc = L.ga_attention_bf16(dit._p(q), dit._p(k), dit._p(vt), dit._p(out), B, H, Nq, Nk, pq, pk, 0.125, 0.0, st)
     torch.cuda.synchronize()
     ref = torch.nn.functional.scaled_dot_product_attention(
         q[:, :Nq].float().view(B, H, Nq, 64), k[:, :Nk].float().view(B, H, Nk, 64),
