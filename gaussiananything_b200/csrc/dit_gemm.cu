@@ -172,7 +172,10 @@ __device__ __forceinline__ void epilogue_head(const GaGemmEpilogue &ep, uint32_t
 
 // Persistent: grid = min(#tiles, #SMs); every role loops over the CTA's tiles.  The TMEM accumulator is double
 // buffered (2*BN columns), so the epilogue of tile i overlaps the TMA/MMA main loop of tile i+1.
-template <int BN>
+// CS > 1: a cluster of CS CTAs works on CS vertically adjacent tiles (same n-block).  Each CTA loads its own A
+// tile and 1/CS of the shared W tile, multicast to every CTA of the cluster, so the L2 -> SM operand traffic per
+// CTA drops from (128 + BN) to (128 + BN/CS) rows per k-block -- the main loop is L2-bandwidth bound otherwise.
+template <int BN, int CS>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                     const GaGemmEpilogue ep, const int M, const int N, const int K)
@@ -187,7 +190,11 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nk = (K + BK - 1) / BK;
     const int num_m = (M + BM - 1) / BM, num_n = (N + BN - 1) / BN;
-    const int tiles = num_m * num_n;
+    const int num_mg = (num_m + CS - 1) / CS;          // groups of CS m-blocks
+    const int tiles = num_mg * num_n;                  // work items per CLUSTER
+    const int crank = CS > 1 ? (int)cluster_ctarank() : 0;
+    const int cid = blockIdx.x / CS, ncl = gridDim.x / CS;
+    constexpr uint16_t kMask = (uint16_t)((1u << CS) - 1);
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tma_a);
@@ -195,7 +202,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     }
     if (warp == 1) {
         if (lane == 0) {
-            for (int s = 0; s < Cfg::kStages; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+            for (int s = 0; s < Cfg::kStages; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], CS); }
             for (int a = 0; a < 2; a++) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], kEpiWarps); }
             fence_barrier_init();
         }
@@ -204,6 +211,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     }
     tc_fence_before();
     __syncthreads();
+    if (CS > 1) cluster_sync_all();                    // peers' barriers exist before anyone multicasts into them
     tc_fence_after();
     const uint32_t tmem = tmem_slot;
     pdl_wait();                     // inputs (A, the residual stream, the gate table) come from earlier kernels
@@ -212,15 +220,21 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     if (warp == 0) {
         if (elect_one()) {
             int it = 0;
-            for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-                const int m0 = (tile % num_m) * BM, n0 = (tile / num_m) * BN;
+            for (int tile = cid; tile < tiles; tile += ncl) {
+                const int m0 = ((tile % num_mg) * CS + crank) * BM, n0 = (tile / num_mg) * BN;
                 for (int kb = 0; kb < nk; kb++, it++) {
                     const int s = it % Cfg::kStages;
                     const uint32_t ph = (it / Cfg::kStages) & 1;
-                    mbar_wait(&empty_bar[s], ph ^ 1);
+                    mbar_wait(&empty_bar[s], ph ^ 1);       // all CS consumers released this stage
                     mbar_expect_tx(&full_bar[s], Cfg::kABytes + Cfg::kBBytes);
                     tma_load_2d(smem_a + s * Cfg::kABytes, &tma_a, &full_bar[s], kb * BK, m0);
-                    tma_load_2d(smem_b + s * Cfg::kBBytes, &tma_b, &full_bar[s], kb * BK, n0);
+                    if (CS == 1) {
+                        tma_load_2d(smem_b + s * Cfg::kBBytes, &tma_b, &full_bar[s], kb * BK, n0);
+                    } else {
+                        constexpr int kPart = Cfg::kBBytes / CS;        // this CTA's slice of the W tile
+                        tma_load_2d_mcast(smem_b + s * Cfg::kBBytes + crank * kPart, &tma_b, &full_bar[s], kb * BK,
+                                          n0 + crank * (BN / CS), kMask);
+                    }
                 }
             }
         }
@@ -228,7 +242,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
         if (elect_one()) {
             constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
             int it = 0, lt = 0;
-            for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, lt++) {
+            for (int tile = cid; tile < tiles; tile += ncl, lt++) {
                 const int a = lt & 1;
                 mbar_wait(&acc_empty[a], ((lt >> 1) & 1) ^ 1);
                 tc_fence_after();
@@ -242,7 +256,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
 #pragma unroll
                     for (int k = 0; k < BK / 16; k++)
                         umma_bf16_ss(tacc, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, (kb | k) != 0);
-                    umma_commit(&empty_bar[s]);     // frees the smem stage when these MMAs retire
+                    if (CS == 1) umma_commit(&empty_bar[s]);            // frees the smem stage when these MMAs retire
+                    else umma_commit_mcast(&empty_bar[s], kMask);       // ... in every CTA that multicasts into it
                 }
                 umma_commit(&acc_full[a]);          // accumulator of this tile complete
             }
@@ -253,8 +268,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
         const int chalf = ew >> 2;                  // which half of the BN columns this warp drains
         const int row = q * 32 + lane;
         int lt = 0;
-        for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, lt++) {
-            const int m0 = (tile % num_m) * BM, n0 = (tile / num_m) * BN;
+        for (int tile = cid; tile < tiles; tile += ncl, lt++) {
+            const int m0 = ((tile % num_mg) * CS + crank) * BM, n0 = (tile / num_mg) * BN;
             const int a = lt & 1;
             mbar_wait(&acc_full[a], (lt >> 1) & 1);
             tc_fence_after();
@@ -286,6 +301,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
         }
     }
     __syncthreads();
+    if (CS > 1) cluster_sync_all();                    // nobody exits while a peer can still write into its smem
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc<Cfg::kTmemCols>(tmem);
@@ -329,18 +345,8 @@ int ga_make_tmap_bf16(CUtensorMap *map, const void *ptr, uint64_t rows, uint64_t
     return r == CUDA_SUCCESS ? 0 : 1000 + (int)r;
 }
 
-template <int BN>
-static int launch_gemm(const CUtensorMap &ta, const CUtensorMap &tb, const GaGemmEpilogue &ep, int M, int N, int K,
-                       cudaStream_t s)
+static int sm_count()
 {
-    using Cfg = GemmCfg<BN>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tn_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             Cfg::kSmem);
-        if (e != cudaSuccess) return (int)e;
-        attr_set = true;
-    }
     static int num_sms = 0;
     if (!num_sms) {
         int dev = 0;
@@ -348,24 +354,59 @@ static int launch_gemm(const CUtensorMap &ta, const CUtensorMap &tb, const GaGem
         cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
         if (num_sms <= 0) num_sms = 148;
     }
-    const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
-    dim3 grid(tiles < num_sms ? tiles : num_sms);
-    return (int)ga_launch_pdl(gemm_bf16_tn_kernel<BN>, grid, dim3(kThreads), (size_t)Cfg::kSmem, s, ta, tb, ep, M, N, K);
+    return num_sms;
+}
+
+template <int BN, int CS>
+static int launch_gemm(const void *A, int lda, const void *W, int ldw, const GaGemmEpilogue &ep, int M, int N, int K,
+                       cudaStream_t s)
+{
+    using Cfg = GemmCfg<BN>;
+    CUtensorMap ta, tb;
+    int rc = ga_make_tmap_bf16(&ta, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, BM);
+    if (rc) return rc;
+    rc = ga_make_tmap_bf16(&tb, W, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, (uint32_t)(BN / CS));
+    if (rc) return rc;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tn_kernel<BN, CS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             Cfg::kSmem);
+        if (e != cudaSuccess) return (int)e;
+        attr_set = true;
+    }
+    const int num_m = (M + BM - 1) / BM, num_n = (N + BN - 1) / BN;
+    const int items = ((num_m + CS - 1) / CS) * num_n;              // work items per cluster
+    int clusters = sm_count() / CS;
+    if (items < clusters) clusters = items;
+    dim3 grid(clusters * CS);
+    if (CS == 1)
+        return (int)ga_launch_pdl(gemm_bf16_tn_kernel<BN, CS>, grid, dim3(kThreads), (size_t)Cfg::kSmem, s, ta, tb, ep, M, N, K);
+    return (int)ga_launch_cluster(gemm_bf16_tn_kernel<BN, CS>, grid, dim3(kThreads), (size_t)Cfg::kSmem, s, (unsigned)CS, ta,
+                                  tb, ep, M, N, K);
 }
 
 extern "C" int ga_gemm_bf16_tn(const void *A, int lda, const void *W, int ldw, int M, int N, int K,
                                const GaGemmEpilogue *epi, int block_n, void *stream)
 {
     if (!A || !W || !epi || M <= 0 || N <= 0 || K <= 0) return GA_ERR_BADARG;
-    if (epi->mode == GA_EPI_HEADS && (N % 64 != 0 || epi->heads <= 0 || block_n < 128)) return GA_ERR_BADARG;
-    if (block_n != 64 && block_n != 128 && block_n != 256) return GA_ERR_BADARG;
-    CUtensorMap ta, tb;
-    int rc = ga_make_tmap_bf16(&ta, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, BM);
-    if (rc) return rc;
-    rc = ga_make_tmap_bf16(&tb, W, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, (uint32_t)block_n);
-    if (rc) return rc;
+    // block_n = tile width {64,128,256} + 1000 * cluster size {1 (default), 2, 4}
+    const int cs = block_n >= 1000 ? block_n / 1000 : 1;
+    const int bn = block_n % 1000;
+    if (epi->mode == GA_EPI_HEADS && (N % 64 != 0 || epi->heads <= 0 || bn < 128)) return GA_ERR_BADARG;
+    if (bn != 64 && bn != 128 && bn != 256) return GA_ERR_BADARG;
     cudaStream_t s = (cudaStream_t)stream;
-    if (block_n == 64) return launch_gemm<64>(ta, tb, *epi, M, N, K, s);
-    if (block_n == 128) return launch_gemm<128>(ta, tb, *epi, M, N, K, s);
-    return launch_gemm<256>(ta, tb, *epi, M, N, K, s);
+    if (cs == 1) {
+        if (bn == 64) return launch_gemm<64, 1>(A, lda, W, ldw, *epi, M, N, K, s);
+        if (bn == 128) return launch_gemm<128, 1>(A, lda, W, ldw, *epi, M, N, K, s);
+        return launch_gemm<256, 1>(A, lda, W, ldw, *epi, M, N, K, s);
+    }
+    if (cs == 2) {
+        if (bn == 128) return launch_gemm<128, 2>(A, lda, W, ldw, *epi, M, N, K, s);
+        if (bn == 256) return launch_gemm<256, 2>(A, lda, W, ldw, *epi, M, N, K, s);
+    }
+    if (cs == 4) {
+        if (bn == 128) return launch_gemm<128, 4>(A, lda, W, ldw, *epi, M, N, K, s);
+        if (bn == 256) return launch_gemm<256, 4>(A, lda, W, ldw, *epi, M, N, K, s);
+    }
+    return GA_ERR_BADARG;
 }

@@ -73,6 +73,23 @@ def _ck(rc, what):
         raise RuntimeError("libga_b200: %s failed with code %d" % (what, rc))
 
 
+_GEMM_CFG_ENV = None
+
+
+def _gemm_config(M, N):
+    """Tile width + 1000 * cluster size (ga_b200.h).  Large problems: 128x256 tiles in clusters of 4 CTAs that share
+    the weight tile by TMA multicast (the main loop is L2->SM bandwidth bound otherwise); small ones: 128x128."""
+    global _GEMM_CFG_ENV
+    if _GEMM_CFG_ENV is None:
+        import os
+        _GEMM_CFG_ENV = os.environ.get("GA_B200_GEMM_CFG", "")
+    if _GEMM_CFG_ENV:
+        big, small = (int(v) for v in _GEMM_CFG_ENV.split(","))
+    else:
+        big, small = 256, 128
+    return big if (M >= 1024 and N >= 512) else small
+
+
 def _round_up(x, m):
     return (x + m - 1) // m * m
 
@@ -336,8 +353,8 @@ class _DiTEngine:
                 w1=b16(mlp[0].weight), b1=f32(mlp[1].bias), w2=b16(mlp[2].weight), b2=f32(mlp[3].bias),
                 # |q.k|/8 <= (sqrt(64) max|wq|)(sqrt(64) max|wk|)/8 for RMS-normalised q, k (+2% for bf16 rounding):
                 # lets the attention kernel skip the running maximum (ga_b200.h: score_bound)
-                ca_bound=8.16 * float(ca.q_norm.weight.abs().max()) * float(ca.k_norm.weight.abs().max()),
-                sa_bound=8.16 * float(sa.q_norm.weight.abs().max()) * float(sa.k_norm.weight.abs().max())))
+                ca_bound=8.16 * float(ca.q_norm.weight.detach().abs().max()) * float(ca.k_norm.weight.detach().abs().max()),
+                sa_bound=8.16 * float(sa.q_norm.weight.detach().abs().max()) * float(sa.k_norm.weight.detach().abs().max())))
         self.w, self.wb = w, blocks
 
     # ---- workspaces for a (B, N, M) problem
@@ -366,8 +383,8 @@ class _DiTEngine:
 
     # ---- launches
     def _gemm(self, A, W, M, N, K, epi, st, bn=None):
-        if bn is None:                       # wide outputs: 128x256 tiles halve the operand re-reads from L2
-            bn = 256 if N >= 2048 else 128
+        if bn is None:
+            bn = _gemm_config(M, N)
         _ck(self.L.ga_gemm_bf16_tn(_p(A), K, _p(W), K, M, N, K, C.byref(epi), bn, st), "ga_gemm_bf16_tn")
 
     def _epi(self, mode, **kw):
