@@ -439,7 +439,7 @@ def run_dit_leg(dev, steps_grid=50, reps=3):
                                                       eng.Np, eng.Np, 0.125, eng.wb[0]["sa_bound"], st))
     wb = eng.wb[0]
     epi = eng._epi(dit.EPI_GELU_BF16, bias=wb["b1"], out=s["hid"], ld_out=4 * D)
-    t_gemm = time_kernel(lambda: Lb.ga_gemm_bf16_tn(dit._p(s["h"]), D, dit._p(wb["w1"]), D, B * N, 4 * D, D, C.byref(epi), 256, st))
+    t_gemm = time_kernel(lambda: Lb.ga_gemm_bf16_tn(dit._p(s["h"]), D, dit._p(wb["w1"]), D, B * N, 4 * D, D, C.byref(epi), 128, st))
     fl_attn = 4.0 * N * N * 64 * B * H
     fl_gemm = 2.0 * B * N * 4 * D * D
     return {"config": "C3: DiT-PixArt-PCD-CLAY-B (L12 D768 H12), N=2048, M=1369, %d-point Euler grid (%d NFE), CFG 4.0, bf16" % (steps_grid, nfe),

@@ -77,8 +77,9 @@ _GEMM_CFG_ENV = None
 
 
 def _gemm_config(M, N):
-    """Tile width + 1000 * cluster size (ga_b200.h).  Large problems: 128x256 tiles in clusters of 4 CTAs that share
-    the weight tile by TMA multicast (the main loop is L2->SM bandwidth bound otherwise); small ones: 128x128."""
+    """Tile width + 1000 * cluster size (ga_b200.h).  Measured on B200 (tools/sweep_gemm.py, profiles/r01_gemm_sweep.txt):
+    128x128 tiles without clusters win on every DiT shape -- the main loop is limited by each SM's own operand
+    ingest, which TMA multicast does not reduce (only cta_group::2 MMA would).  GA_B200_GEMM_CFG overrides."""
     global _GEMM_CFG_ENV
     if _GEMM_CFG_ENV is None:
         import os
@@ -86,7 +87,7 @@ def _gemm_config(M, N):
     if _GEMM_CFG_ENV:
         big, small = (int(v) for v in _GEMM_CFG_ENV.split(","))
     else:
-        big, small = 256, 128
+        big, small = 128, 128
     return big if (M >= 1024 and N >= 512) else small
 
 
