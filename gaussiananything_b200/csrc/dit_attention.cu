@@ -33,7 +33,8 @@ constexpr int kKBytes = AK * HD * 2;            // 16 KB per stage, 2 stages
 constexpr int kVBytes = HD * AK * 2;            // 16 KB (two 64-key sub-tiles of 8 KB), 1 stage
 constexpr int kPBytes = AQ * AK * 2;            // 32 KB (two 64-key sub-tiles of 16 KB), 1 buffer
 constexpr int kSmemAttn = kQBytes + 2 * kKBytes + kVBytes + kPBytes + 1024;     // 97 KB -> 2 CTAs / SM
-constexpr int kAttnThreads = 192;
+constexpr int kAttnThreads = 192;          // online softmax: TMA warp, MMA warp, 4 softmax warps (one row per thread)
+constexpr int kAttnThreadsStatic = 320;    // static bound: 8 softmax warps, two threads per row (64 keys each)
 constexpr uint32_t kTmemColsAttn = 256;         // S: 128 columns, O_blk: 64 columns; 2 CTAs share the SM's 512
 
 __device__ __forceinline__ uint32_t pack2(float a, float b)
@@ -48,21 +49,6 @@ __device__ __forceinline__ float ex2_fast(float x)
     return r;
 }
 
-// 2^x on the FMA/ALU pipes (no MUFU): round-to-nearest split x = n + f via the 1.5*2^23 magic constant, a
-// degree-3 minimax polynomial for 2^f on [-0.5, 0.5] (max rel. error 7.5e-5, far below bf16's 2^-9) and an
-// exponent add.  The MUFU unit is the bottleneck of head_dim-64 attention (128x128 exponentials per 2x256
-// tensor-pipe cycles), so every other element takes this path and the two pipes share the load.
-__device__ __forceinline__ float ex2_poly(float x)
-{
-    x = fmaxf(x, -125.0f);
-    const float t = x + 12582912.0f;
-    const float f = x - (t - 12582912.0f);
-    float p = fmaf(f, 0.0551715307f, 0.2426111102f);
-    p = fmaf(p, f, 0.6932610273f);
-    p = fmaf(p, f, 0.9999280572f);
-    return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
-}
-
 // Two CTAs are co-resident per SM (97 KB smem, 256 TMEM columns, <=168 registers): while one CTA's softmax
 // warps keep the MUFU/FMA pipes busy, the other CTA's MMAs and TMA loads run -- the hardware interleaves the
 // two dependency chains, so the kernel needs no intra-CTA ping-pong.
@@ -72,7 +58,7 @@ __device__ __forceinline__ float ex2_poly(float x)
 // maximum, no rescaling and no per-block read-out of O are needed: P*V accumulates in TMEM over all key blocks
 // and S is read from TMEM exactly once.  Mathematically identical to softmax (the constant cancels in O / l).
 template <bool kStatic>
-__global__ void __launch_bounds__(kAttnThreads, 2)
+__global__ void __launch_bounds__(kStatic ? kAttnThreadsStatic : kAttnThreads, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_k,
                 const __grid_constant__ CUtensorMap tma_vt, __nv_bfloat16 *__restrict__ out,
                 const int Nq, const int Nk, const int pitch_q, const int pitch_k, const int heads,
@@ -81,6 +67,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint64_t q_full, k_full[2], k_empty[2], v_full, v_empty, s_full, p_full, o_full, o_empty, p_empty;
     __shared__ uint32_t tmem_slot;
+    __shared__ float s_lsum[2][AQ];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t *sQ = smem;
     uint8_t *sK = sQ + kQBytes;
@@ -101,7 +88,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
             for (int s = 0; s < 2; s++) { mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1); }
             mbar_init(&v_full, 1); mbar_init(&v_empty, 1);
             mbar_init(&s_full, 1); mbar_init(&o_full, 1);
-            mbar_init(&p_full, 128); mbar_init(&o_empty, 128); mbar_init(&p_empty, 1);
+            mbar_init(&p_full, kStatic ? 256 : 128); mbar_init(&o_empty, 128); mbar_init(&p_empty, 1);
             fence_barrier_init();
         }
         __syncwarp();
@@ -199,51 +186,71 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
         };
 
         if (kStatic) {
+            // two threads per query row: this one handles keys [half*64, half*64+64) of every block, i.e. exactly
+            // one 64-key sub-tile of P; no running maximum means the two never have to talk until the end.
+            const int half = (warp - 2) >> 2;
             float ls0 = 0.f, ls1 = 0.f, ls2 = 0.f, ls3 = 0.f;
+            uint8_t *psub = prow + half * (kPBytes / 2);
+            const uint32_t tS_mine = tS + lane_off + half * 64;
             for (int j = 0; j < nb; j++) {
                 mbar_wait(&s_full, j & 1);
                 tc_fence_after();
-                const int kbase = j * AK;
-                const bool ragged = kbase + AK > Nk;
-#pragma unroll 1
-                for (int c = 0; c < AK; c += 32) {
-                    uint32_t r[32];
-                    tmem_ld_32x32b_x32(tS + lane_off + c, r);
-                    tmem_ld_wait();
-                    float p[32];
+                const int kbase = j * AK + half * 64;
+                const bool ragged = kbase + 64 > Nk;
+                uint32_t r0[32], r1[32];
+                tmem_ld_32x32b_x32(tS_mine, r0);          // both chunks in flight before the first use
+                tmem_ld_32x32b_x32(tS_mine + 32, r1);
+                tmem_ld_wait();
+                float p[32];
 #pragma unroll
-                    for (int i = 0; i < 32; i++) {
-                        const float v = (ragged && kbase + c + i >= Nk) ? -INFINITY : __uint_as_float(r[i]);
-                        const float xx = fmaf(v, scale_log2, -bound_log2);
-                        p[i] = (i & 1) ? ex2_poly(xx) : ex2_fast(xx);
-                    }
-#pragma unroll
-                    for (int i = 0; i < 32; i += 4) { ls0 += p[i]; ls1 += p[i + 1]; ls2 += p[i + 2]; ls3 += p[i + 3]; }
-                    if (c == 0 && j > 0) mbar_wait(&p_empty, (j - 1) & 1);      // P*V of the previous block retired
-#pragma unroll
-                    for (int g = 0; g < 4; g++) {
-                        const int c8 = (c >> 3) + g;
-                        const int sub = c8 >> 3, q16 = c8 & 7;
-                        uint4 *dst = reinterpret_cast<uint4 *>(prow + sub * (kPBytes / 2) + ((q16 ^ (row & 7)) << 4));
-                        *dst = make_uint4(pack2(p[8 * g], p[8 * g + 1]), pack2(p[8 * g + 2], p[8 * g + 3]),
-                                          pack2(p[8 * g + 4], p[8 * g + 5]), pack2(p[8 * g + 6], p[8 * g + 7]));
-                    }
+                for (int i = 0; i < 32; i++) {
+                    const float v = (ragged && kbase + i >= Nk) ? -INFINITY : __uint_as_float(r0[i]);
+                    p[i] = ex2_fast(fmaf(v, scale_log2, -bound_log2));
                 }
+#pragma unroll
+                for (int i = 0; i < 32; i += 4) { ls0 += p[i]; ls1 += p[i + 1]; ls2 += p[i + 2]; ls3 += p[i + 3]; }
+                if (j > 0) mbar_wait(&p_empty, (j - 1) & 1);      // P*V of the previous block has retired
+#pragma unroll
+                for (int g = 0; g < 4; g++)
+                    *reinterpret_cast<uint4 *>(psub + ((g ^ (row & 7)) << 4)) =
+                        make_uint4(pack2(p[8 * g], p[8 * g + 1]), pack2(p[8 * g + 2], p[8 * g + 3]),
+                                   pack2(p[8 * g + 4], p[8 * g + 5]), pack2(p[8 * g + 6], p[8 * g + 7]));
+#pragma unroll
+                for (int i = 0; i < 32; i++) {
+                    const float v = (ragged && kbase + 32 + i >= Nk) ? -INFINITY : __uint_as_float(r1[i]);
+                    p[i] = ex2_fast(fmaf(v, scale_log2, -bound_log2));
+                }
+#pragma unroll
+                for (int i = 0; i < 32; i += 4) { ls0 += p[i]; ls1 += p[i + 1]; ls2 += p[i + 2]; ls3 += p[i + 3]; }
+#pragma unroll
+                for (int g = 0; g < 4; g++)
+                    *reinterpret_cast<uint4 *>(psub + (((4 + g) ^ (row & 7)) << 4)) =
+                        make_uint4(pack2(p[8 * g], p[8 * g + 1]), pack2(p[8 * g + 2], p[8 * g + 3]),
+                                   pack2(p[8 * g + 4], p[8 * g + 5]), pack2(p[8 * g + 6], p[8 * g + 7]));
                 fence_proxy_async_smem();
                 tc_fence_before();
                 mbar_arrive(&p_full);
             }
-            l_run = (ls0 + ls1) + (ls2 + ls3);
+            s_lsum[half][row] = (ls0 + ls1) + (ls2 + ls3);
+            asm volatile("bar.sync 1, 256;\n" ::: "memory");      // the 8 softmax warps only
+            const float inv = 1.0f / (s_lsum[0][row] + s_lsum[1][row]);
             mbar_wait(&o_full, 0);
             tc_fence_after();
+            uint32_t r[32];
+            tmem_ld_32x32b_x32(tO + lane_off + half * 32, r);      // this thread writes head dims [half*32, +32)
+            tmem_ld_wait();
+            const int q = q0 + row;
+            if (q < Nq) {
+                const int b = bh / heads, h = bh % heads;
+                uint4 *dst = reinterpret_cast<uint4 *>(out + ((size_t)b * Nq + q) * (size_t)(heads * HD) + h * HD + half * 32);
 #pragma unroll
-            for (int h2 = 0; h2 < 2; h2++) {
-                uint32_t r[32];
-                tmem_ld_32x32b_x32(tO + lane_off + h2 * 32, r);
-                tmem_ld_wait();
-#pragma unroll
-                for (int i = 0; i < 32; i++) o_acc[h2 * 32 + i] = __uint_as_float(r[i]);
+                for (int i = 0; i < 4; i++)
+                    dst[i] = make_uint4(pack2(__uint_as_float(r[8 * i]) * inv, __uint_as_float(r[8 * i + 1]) * inv),
+                                        pack2(__uint_as_float(r[8 * i + 2]) * inv, __uint_as_float(r[8 * i + 3]) * inv),
+                                        pack2(__uint_as_float(r[8 * i + 4]) * inv, __uint_as_float(r[8 * i + 5]) * inv),
+                                        pack2(__uint_as_float(r[8 * i + 6]) * inv, __uint_as_float(r[8 * i + 7]) * inv));
             }
+            tc_fence_before();
         } else {
         for (int j = 0; j < nb; j++) {
             mbar_wait(&s_full, j & 1);
@@ -281,7 +288,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
                 for (int i = 0; i < 32; i++) {
                     const float v = (ragged && kbase + c + i >= Nk) ? -INFINITY : __uint_as_float(r[i]);
                     const float xx = fmaf(v, scale_log2, -m_new);
-                    p[i] = (i & 1) ? ex2_poly(xx) : ex2_fast(xx);
+                    p[i] = ex2_fast(xx);
                     lsum += p[i];
                 }
 #pragma unroll
@@ -299,7 +306,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
             mbar_arrive(&p_full);
         }
         accumulate_o(nb - 1, corr);
-        }
         const int q = q0 + row;
         if (q < Nq) {
             const float inv = 1.0f / l_run;
@@ -313,6 +319,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
                                     pack2(o_acc[8 * i + 6] * inv, o_acc[8 * i + 7] * inv));
         }
         tc_fence_before();
+        }
     }
     __syncthreads();
     if (warp == 1) {
@@ -352,7 +359,7 @@ extern "C" int ga_attention_bf16(const void *Q, const void *K, const void *Vt, v
     const bool use_static = score_bound > 0.f && score_bound <= 40.f;
     __nv_bfloat16 *o = reinterpret_cast<__nv_bfloat16 *>(out);
     if (use_static)
-        return (int)ga_launch_pdl(attn_fwd_kernel<true>, grid, dim3(kAttnThreads), (size_t)kSmemAttn, (cudaStream_t)stream,
+        return (int)ga_launch_pdl(attn_fwd_kernel<true>, grid, dim3(kAttnThreadsStatic), (size_t)kSmemAttn, (cudaStream_t)stream,
                                   tq, tk, tv, o, Nq, Nk, pitch_q, pitch_k, heads, scale_log2, score_bound * log2e);
     return (int)ga_launch_pdl(attn_fwd_kernel<false>, grid, dim3(kAttnThreads), (size_t)kSmemAttn, (cudaStream_t)stream,
                               tq, tk, tv, o, Nq, Nk, pitch_q, pitch_k, heads, scale_log2, 0.0f);
