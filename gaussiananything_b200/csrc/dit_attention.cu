@@ -34,7 +34,7 @@ constexpr int kVBytes = HD * AK * 2;            // 16 KB (two 64-key sub-tiles o
 constexpr int kPBytes = AQ * AK * 2;            // 32 KB (two 64-key sub-tiles of 16 KB), 1 buffer
 constexpr int kSmemAttn = kQBytes + 2 * kKBytes + kVBytes + kPBytes + 1024;     // 97 KB -> 2 CTAs / SM
 constexpr int kAttnThreads = 192;          // online softmax: TMA warp, MMA warp, 4 softmax warps (one row per thread)
-constexpr int kAttnThreadsStatic = 320;    // static bound: 8 softmax warps, two threads per row (64 keys each)
+// static bound: NS threads per query row (each handles 128/NS keys): block = 64 + 128*NS threads
 constexpr uint32_t kTmemColsAttn = 256;         // S: 128 columns, O_blk: 64 columns; 2 CTAs share the SM's 512
 
 __device__ __forceinline__ uint32_t pack2(float a, float b)
@@ -57,8 +57,8 @@ __device__ __forceinline__ float ex2_fast(float x)
 // RMS-normalised: |q.k| <= 64 max|w_q| max|w_k|).  exp2(s*scale - bound) then never overflows, so no running
 // maximum, no rescaling and no per-block read-out of O are needed: P*V accumulates in TMEM over all key blocks
 // and S is read from TMEM exactly once.  Mathematically identical to softmax (the constant cancels in O / l).
-template <bool kStatic>
-__global__ void __launch_bounds__(kStatic ? kAttnThreadsStatic : kAttnThreads, 2)
+template <bool kStatic, int kRowSplit>
+__global__ void __launch_bounds__(kStatic ? 64 + 128 * kRowSplit : kAttnThreads, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_k,
                 const __grid_constant__ CUtensorMap tma_vt, __nv_bfloat16 *__restrict__ out,
                 const int Nq, const int Nk, const int pitch_q, const int pitch_k, const int heads,
@@ -67,7 +67,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint64_t q_full, k_full[2], k_empty[2], v_full, v_empty, s_full, p_full, o_full, o_empty, p_empty;
     __shared__ uint32_t tmem_slot;
-    __shared__ float s_lsum[2][AQ];
+    __shared__ float s_lsum[kRowSplit][AQ];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t *sQ = smem;
     uint8_t *sK = sQ + kQBytes;
@@ -88,7 +88,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
             for (int s = 0; s < 2; s++) { mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1); }
             mbar_init(&v_full, 1); mbar_init(&v_empty, 1);
             mbar_init(&s_full, 1); mbar_init(&o_full, 1);
-            mbar_init(&p_full, kStatic ? 256 : 128); mbar_init(&o_empty, 128); mbar_init(&p_empty, 1);
+            mbar_init(&p_full, kStatic ? 128 * kRowSplit : 128); mbar_init(&o_empty, 128); mbar_init(&p_empty, 1);
             fence_barrier_init();
         }
         __syncwarp();
@@ -186,69 +186,85 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
         };
 
         if (kStatic) {
-            // two threads per query row: this one handles keys [half*64, half*64+64) of every block, i.e. exactly
-            // one 64-key sub-tile of P; no running maximum means the two never have to talk until the end.
-            const int half = (warp - 2) >> 2;
+            // kRowSplit threads per query row: this one handles keys [part*KP, part*KP+KP) of every block; with no
+            // running maximum the threads of a row never have to talk until the very end.
+            constexpr int KP = AK / kRowSplit;                 // 32 or 64 keys per thread
+            const int part = (warp - 2) >> 2;
             float ls0 = 0.f, ls1 = 0.f, ls2 = 0.f, ls3 = 0.f;
-            uint8_t *psub = prow + half * (kPBytes / 2);
-            const uint32_t tS_mine = tS + lane_off + half * 64;
+            // P sub-tile (64 keys each) and first 16-byte chunk inside it
+            uint8_t *psub = prow + ((part * KP) >> 6) * (kPBytes / 2);
+            const int chunk0 = ((part * KP) & 63) >> 3;
+            const uint32_t tS_mine = tS + lane_off + part * KP;
             for (int j = 0; j < nb; j++) {
                 mbar_wait(&s_full, j & 1);
                 tc_fence_after();
-                const int kbase = j * AK + half * 64;
-                const bool ragged = kbase + 64 > Nk;
-                uint32_t r0[32], r1[32];
-                tmem_ld_32x32b_x32(tS_mine, r0);          // both chunks in flight before the first use
-                tmem_ld_32x32b_x32(tS_mine + 32, r1);
+                const int kbase = j * AK + part * KP;
+                const bool ragged = kbase + KP > Nk;
+                uint32_t r[KP / 32][32];
+#pragma unroll
+                for (int h2 = 0; h2 < KP / 32; h2++) tmem_ld_32x32b_x32(tS_mine + h2 * 32, r[h2]);   // all loads in flight
                 tmem_ld_wait();
-                float p[32];
 #pragma unroll
-                for (int i = 0; i < 32; i++) {
-                    const float v = (ragged && kbase + i >= Nk) ? -INFINITY : __uint_as_float(r0[i]);
-                    p[i] = ex2_fast(fmaf(v, scale_log2, -bound_log2));
+                for (int h2 = 0; h2 < KP / 32; h2++) {
+                    // exponentials overwrite the score registers (keeps the live set at 32 values)
+#pragma unroll
+                    for (int i = 0; i < 32; i++) {
+                        float v = __uint_as_float(r[h2][i]);
+                        if (ragged && kbase + h2 * 32 + i >= Nk) v = -INFINITY;
+                        r[h2][i] = __float_as_uint(ex2_fast(fmaf(v, scale_log2, -bound_log2)));
+                    }
+#pragma unroll
+                    for (int i = 0; i < 32; i += 4) {
+                        ls0 += __uint_as_float(r[h2][i]); ls1 += __uint_as_float(r[h2][i + 1]);
+                        ls2 += __uint_as_float(r[h2][i + 2]); ls3 += __uint_as_float(r[h2][i + 3]);
+                    }
+                    if (h2 == 0 && j > 0) mbar_wait(&p_empty, (j - 1) & 1);   // P*V of the previous block has retired
+#pragma unroll
+                    for (int g = 0; g < 4; g++) {
+                        const uint32_t *pp = &r[h2][8 * g];
+                        *reinterpret_cast<uint4 *>(psub + (((chunk0 + h2 * 4 + g) ^ (row & 7)) << 4)) =
+                            make_uint4(pack2(__uint_as_float(pp[0]), __uint_as_float(pp[1])),
+                                       pack2(__uint_as_float(pp[2]), __uint_as_float(pp[3])),
+                                       pack2(__uint_as_float(pp[4]), __uint_as_float(pp[5])),
+                                       pack2(__uint_as_float(pp[6]), __uint_as_float(pp[7])));
+                    }
                 }
-#pragma unroll
-                for (int i = 0; i < 32; i += 4) { ls0 += p[i]; ls1 += p[i + 1]; ls2 += p[i + 2]; ls3 += p[i + 3]; }
-                if (j > 0) mbar_wait(&p_empty, (j - 1) & 1);      // P*V of the previous block has retired
-#pragma unroll
-                for (int g = 0; g < 4; g++)
-                    *reinterpret_cast<uint4 *>(psub + ((g ^ (row & 7)) << 4)) =
-                        make_uint4(pack2(p[8 * g], p[8 * g + 1]), pack2(p[8 * g + 2], p[8 * g + 3]),
-                                   pack2(p[8 * g + 4], p[8 * g + 5]), pack2(p[8 * g + 6], p[8 * g + 7]));
-#pragma unroll
-                for (int i = 0; i < 32; i++) {
-                    const float v = (ragged && kbase + 32 + i >= Nk) ? -INFINITY : __uint_as_float(r1[i]);
-                    p[i] = ex2_fast(fmaf(v, scale_log2, -bound_log2));
-                }
-#pragma unroll
-                for (int i = 0; i < 32; i += 4) { ls0 += p[i]; ls1 += p[i + 1]; ls2 += p[i + 2]; ls3 += p[i + 3]; }
-#pragma unroll
-                for (int g = 0; g < 4; g++)
-                    *reinterpret_cast<uint4 *>(psub + (((4 + g) ^ (row & 7)) << 4)) =
-                        make_uint4(pack2(p[8 * g], p[8 * g + 1]), pack2(p[8 * g + 2], p[8 * g + 3]),
-                                   pack2(p[8 * g + 4], p[8 * g + 5]), pack2(p[8 * g + 6], p[8 * g + 7]));
                 fence_proxy_async_smem();
                 tc_fence_before();
                 mbar_arrive(&p_full);
             }
-            s_lsum[half][row] = (ls0 + ls1) + (ls2 + ls3);
-            asm volatile("bar.sync 1, 256;\n" ::: "memory");      // the 8 softmax warps only
-            const float inv = 1.0f / (s_lsum[0][row] + s_lsum[1][row]);
+            s_lsum[part][row] = (ls0 + ls1) + (ls2 + ls3);
+            asm volatile("bar.sync 1, %0;\n" ::"n"(128 * kRowSplit) : "memory");      // the softmax warps only
+            float lt = 0.f;
+#pragma unroll
+            for (int k = 0; k < kRowSplit; k++) lt += s_lsum[k][row];
+            const float inv = 1.0f / lt;
             mbar_wait(&o_full, 0);
             tc_fence_after();
-            uint32_t r[32];
-            tmem_ld_32x32b_x32(tO + lane_off + half * 32, r);      // this thread writes head dims [half*32, +32)
-            tmem_ld_wait();
+            constexpr int OC = HD / kRowSplit;                 // head dims this thread writes out
             const int q = q0 + row;
-            if (q < Nq) {
-                const int b = bh / heads, h = bh % heads;
-                uint4 *dst = reinterpret_cast<uint4 *>(out + ((size_t)b * Nq + q) * (size_t)(heads * HD) + h * HD + half * 32);
+            const int ob = bh / heads, oh = bh % heads;
+            uint4 *dst = reinterpret_cast<uint4 *>(out + ((size_t)ob * Nq + q) * (size_t)(heads * HD) + oh * HD + part * OC);
+            auto write_out = [&](const auto &ro) {
+                if (q < Nq) {
 #pragma unroll
-                for (int i = 0; i < 4; i++)
-                    dst[i] = make_uint4(pack2(__uint_as_float(r[8 * i]) * inv, __uint_as_float(r[8 * i + 1]) * inv),
-                                        pack2(__uint_as_float(r[8 * i + 2]) * inv, __uint_as_float(r[8 * i + 3]) * inv),
-                                        pack2(__uint_as_float(r[8 * i + 4]) * inv, __uint_as_float(r[8 * i + 5]) * inv),
-                                        pack2(__uint_as_float(r[8 * i + 6]) * inv, __uint_as_float(r[8 * i + 7]) * inv));
+                    for (int i = 0; i < OC / 8; i++)
+                        dst[i] = make_uint4(pack2(__uint_as_float(ro[8 * i]) * inv, __uint_as_float(ro[8 * i + 1]) * inv),
+                                            pack2(__uint_as_float(ro[8 * i + 2]) * inv, __uint_as_float(ro[8 * i + 3]) * inv),
+                                            pack2(__uint_as_float(ro[8 * i + 4]) * inv, __uint_as_float(ro[8 * i + 5]) * inv),
+                                            pack2(__uint_as_float(ro[8 * i + 6]) * inv, __uint_as_float(ro[8 * i + 7]) * inv));
+                }
+            };
+            if constexpr (OC == 32) {
+                uint32_t ro[32];
+                tmem_ld_32x32b_x32(tO + lane_off + part * OC, ro);
+                tmem_ld_wait();
+                write_out(ro);
+            } else {
+                uint32_t ro[16];
+                tmem_ld_32x32b_x16(tO + lane_off + part * OC, ro);
+                tmem_ld_wait();
+                write_out(ro);
             }
             tc_fence_before();
         } else {
@@ -345,11 +361,16 @@ extern "C" int ga_attention_bf16(const void *Q, const void *K, const void *Vt, v
     rc = ga_make_tmap_bf16(&tv, Vt, BH * HD, (uint64_t)pitch_k, (uint64_t)pitch_k, HD);
     if (rc) return rc;
     static bool attr_set = false;
+    static int split = 2;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemAttn);
+        cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemAttn);
         if (e != cudaSuccess) return (int)e;
-        e = cudaFuncSetAttribute(attn_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemAttn);
+        e = cudaFuncSetAttribute(attn_fwd_kernel<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemAttn);
         if (e != cudaSuccess) return (int)e;
+        e = cudaFuncSetAttribute(attn_fwd_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemAttn);
+        if (e != cudaSuccess) return (int)e;
+        const char *sp = getenv("GA_B200_ATTN_SPLIT");
+        if (sp && sp[0] == '4') split = 4;
         attr_set = true;
     }
     dim3 grid((Nq + AQ - 1) / AQ, (unsigned)BH);
@@ -358,9 +379,12 @@ extern "C" int ga_attention_bf16(const void *Q, const void *K, const void *Vt, v
     // static-bound softmax only while exp(-2*bound) stays far from the fp32/bf16 underflow range
     const bool use_static = score_bound > 0.f && score_bound <= 40.f;
     __nv_bfloat16 *o = reinterpret_cast<__nv_bfloat16 *>(out);
-    if (use_static)
-        return (int)ga_launch_pdl(attn_fwd_kernel<true>, grid, dim3(kAttnThreadsStatic), (size_t)kSmemAttn, (cudaStream_t)stream,
+    if (use_static && split == 4)
+        return (int)ga_launch_pdl(attn_fwd_kernel<true, 4>, grid, dim3(64 + 128 * 4), (size_t)kSmemAttn, (cudaStream_t)stream,
                                   tq, tk, tv, o, Nq, Nk, pitch_q, pitch_k, heads, scale_log2, score_bound * log2e);
-    return (int)ga_launch_pdl(attn_fwd_kernel<false>, grid, dim3(kAttnThreads), (size_t)kSmemAttn, (cudaStream_t)stream,
+    if (use_static)
+        return (int)ga_launch_pdl(attn_fwd_kernel<true, 2>, grid, dim3(64 + 128 * 2), (size_t)kSmemAttn, (cudaStream_t)stream,
+                                  tq, tk, tv, o, Nq, Nk, pitch_q, pitch_k, heads, scale_log2, score_bound * log2e);
+    return (int)ga_launch_pdl(attn_fwd_kernel<false, 1>, grid, dim3(kAttnThreads), (size_t)kSmemAttn, (cudaStream_t)stream,
                               tq, tk, tv, o, Nq, Nk, pitch_q, pitch_k, heads, scale_log2, 0.0f);
 }

@@ -308,6 +308,147 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     }
 }
 
+// ---------------------------------------------------------------------------
+// CTA-pair variant (tcgen05 cta_group::2): a cluster of two CTAs computes a 256 x BN tile.  Each CTA stages its own
+// 128 rows of A and HALF of the W tile (BN/2 rows), so the operand bytes an SM has to ingest per MMA cycle halve
+// for W -- the 1-CTA kernel's main loop is bound by exactly that ingest.  The leader issues one M=256 MMA per
+// k-step; commits are multicast to both CTAs' barriers; both CTAs run their own TMA producer and epilogue.
+// ---------------------------------------------------------------------------
+template <int BN> struct PairCfg {
+    static constexpr int kABytes = BM * BK * 2;                 // 16 KB
+    static constexpr int kBBytes = (BN / 2) * BK * 2;           // this CTA's half of the W tile
+    static constexpr int kStages = (BN >= 256) ? 6 : 8;
+    static constexpr int kSmem = kStages * (kABytes + kBBytes) + 1024;
+    static constexpr int kTmemCols = 2 * BN;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_bf16_tn_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+                         const GaGemmEpilogue ep, const int M, const int N, const int K)
+{
+    using Cfg = PairCfg<BN>;
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ uint64_t full_bar[Cfg::kStages], empty_bar[Cfg::kStages], acc_full[2], acc_empty[2];
+    __shared__ uint32_t tmem_slot;
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t *smem_a = smem, *smem_b = smem + Cfg::kStages * Cfg::kABytes;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nk = (K + BK - 1) / BK;
+    const int num_m = (M + BM - 1) / BM, num_n = (N + BN - 1) / BN;
+    const int num_mg = (num_m + 1) / 2;
+    const int tiles = num_mg * num_n;                   // work items per pair
+    const int crank = (int)cluster_ctarank();
+    const bool leader = crank == 0;
+    const int cid = blockIdx.x >> 1, ncl = gridDim.x >> 1;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tma_a);
+        prefetch_tmap(&tma_b);
+    }
+    if (warp == 1) {
+        if (lane == 0) {
+            for (int s = 0; s < Cfg::kStages; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+            for (int a = 0; a < 2; a++) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 2 * kEpiWarps); }
+            fence_barrier_init();
+        }
+        __syncwarp();
+        tmem_alloc_2cta<Cfg::kTmemCols>(&tmem_slot);
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+
+    if (warp == 0) {
+        if (elect_one()) {
+            int it = 0;
+            for (int tile = cid; tile < tiles; tile += ncl) {
+                const int m0 = ((tile % num_mg) * 2 + crank) * BM, n0 = (tile / num_mg) * BN + crank * (BN / 2);
+                for (int kb = 0; kb < nk; kb++, it++) {
+                    const int s = it % Cfg::kStages;
+                    const uint32_t ph = (it / Cfg::kStages) & 1;
+                    mbar_wait(&empty_bar[s], ph ^ 1);
+                    if (leader) mbar_expect_tx(&full_bar[s], 2 * (Cfg::kABytes + Cfg::kBBytes));   // both CTAs' bytes
+                    tma_load_2d_2cta(smem_a + s * Cfg::kABytes, &tma_a, &full_bar[s], kb * BK, m0);
+                    tma_load_2d_2cta(smem_b + s * Cfg::kBBytes, &tma_b, &full_bar[s], kb * BK, n0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (leader && elect_one()) {
+            constexpr uint32_t idesc = umma_idesc_bf16(2 * BM, BN);
+            int it = 0, lt = 0;
+            for (int tile = cid; tile < tiles; tile += ncl, lt++) {
+                const int a = lt & 1;
+                mbar_wait(&acc_empty[a], ((lt >> 1) & 1) ^ 1);      // both CTAs' epilogues drained this accumulator
+                tc_fence_after();
+                const uint32_t tacc = tmem + (uint32_t)(a * BN);
+                for (int kb = 0; kb < nk; kb++, it++) {
+                    const int s = it % Cfg::kStages;
+                    mbar_wait(&full_bar[s], (it / Cfg::kStages) & 1);
+                    tc_fence_after();
+                    const uint64_t ad = umma_desc_k_sw128(smem_u32(smem_a + s * Cfg::kABytes));
+                    const uint64_t bd = umma_desc_k_sw128(smem_u32(smem_b + s * Cfg::kBBytes));
+#pragma unroll
+                    for (int k = 0; k < BK / 16; k++)
+                        umma_bf16_ss_2cta(tacc, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+                    umma_commit_2cta(&empty_bar[s]);
+                }
+                umma_commit_2cta(&acc_full[a]);
+            }
+        }
+    } else {
+        const int ew = warp - 2;
+        const int q = warp & 3;
+        const int chalf = ew >> 2;
+        const int row = q * 32 + lane;
+        int lt = 0;
+        for (int tile = cid; tile < tiles; tile += ncl, lt++) {
+            const int m0 = ((tile % num_mg) * 2 + crank) * BM, n0 = (tile / num_mg) * BN;
+            const int a = lt & 1;
+            mbar_wait(&acc_full[a], (lt >> 1) & 1);
+            tc_fence_after();
+            const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * BN);
+            const int m = m0 + row;
+            if (ep.mode == GA_EPI_HEADS) {
+#pragma unroll 1
+                for (int c = chalf * (BN / 2); c < (chalf + 1) * (BN / 2); c += 64)
+                    if (n0 + c < N) epilogue_head(ep, trow + c, m, n0 + c, M);
+            } else {
+#pragma unroll 1
+                for (int c = chalf * (BN / 2); c < (chalf + 1) * (BN / 2); c += 32) {
+                    if (n0 + c >= N) break;
+                    uint32_t r[32];
+                    tmem_ld_32x32b_x32(trow + c, r);
+                    tmem_ld_wait();
+                    if (m < M) {
+                        float v[32];
+#pragma unroll
+                        for (int i = 0; i < 32; i++)
+                            v[i] = __uint_as_float(r[i]) + ((ep.bias && n0 + c + i < N) ? __ldg(ep.bias + n0 + c + i) : 0.f);
+                        epilogue32(ep, m, n0 + c, N, v);
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                if (leader) mbar_arrive(&acc_empty[a]);
+                else mbar_arrive_remote(&acc_empty[a], 0);
+            }
+        }
+    }
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc_2cta<Cfg::kTmemCols>(tmem);
+    }
+}
+
 // ---- host side -------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
@@ -385,11 +526,36 @@ static int launch_gemm(const void *A, int lda, const void *W, int ldw, const GaG
                                   tb, ep, M, N, K);
 }
 
+template <int BN>
+static int launch_gemm_pair(const void *A, int lda, const void *W, int ldw, const GaGemmEpilogue &ep, int M, int N, int K,
+                            cudaStream_t s)
+{
+    using Cfg = PairCfg<BN>;
+    CUtensorMap ta, tb;
+    int rc = ga_make_tmap_bf16(&ta, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, BM);
+    if (rc) return rc;
+    rc = ga_make_tmap_bf16(&tb, W, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, (uint32_t)(BN / 2));
+    if (rc) return rc;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tn_pair_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             Cfg::kSmem);
+        if (e != cudaSuccess) return (int)e;
+        attr_set = true;
+    }
+    const int num_m = (M + BM - 1) / BM, num_n = (N + BN - 1) / BN;
+    const int items = ((num_m + 1) / 2) * num_n;
+    int pairs = sm_count() / 2;
+    if (items < pairs) pairs = items;
+    return (int)ga_launch_cluster(gemm_bf16_tn_pair_kernel<BN>, dim3(pairs * 2), dim3(kThreads), (size_t)Cfg::kSmem, s, 2u, ta,
+                                  tb, ep, M, N, K);
+}
+
 extern "C" int ga_gemm_bf16_tn(const void *A, int lda, const void *W, int ldw, int M, int N, int K,
                                const GaGemmEpilogue *epi, int block_n, void *stream)
 {
     if (!A || !W || !epi || M <= 0 || N <= 0 || K <= 0) return GA_ERR_BADARG;
-    // block_n = tile width {64,128,256} + 1000 * cluster size {1 (default), 2, 4}
+    // block_n = tile width {64,128,256} + 1000 * cluster size {1 (default), 2, 4}; 9000 + width = CTA pair
     const int cs = block_n >= 1000 ? block_n / 1000 : 1;
     const int bn = block_n % 1000;
     if (epi->mode == GA_EPI_HEADS && (N % 64 != 0 || epi->heads <= 0 || bn < 128)) return GA_ERR_BADARG;
@@ -407,6 +573,10 @@ extern "C" int ga_gemm_bf16_tn(const void *A, int lda, const void *W, int ldw, i
     if (cs == 4) {
         if (bn == 128) return launch_gemm<128, 4>(A, lda, W, ldw, *epi, M, N, K, s);
         if (bn == 256) return launch_gemm<256, 4>(A, lda, W, ldw, *epi, M, N, K, s);
+    }
+    if (cs == 9) {          // 9xxx: CTA pair (cta_group::2), 256 x bn tile per pair
+        if (bn == 128) return launch_gemm_pair<128>(A, lda, W, ldw, *epi, M, N, K, s);
+        if (bn == 256) return launch_gemm_pair<256>(A, lda, W, ldw, *epi, M, N, K, s);
     }
     return GA_ERR_BADARG;
 }
