@@ -327,6 +327,13 @@ def run_gpu(args):
         else:
             dom, dom_bytes = "render_fwd", bytes_k3
         achieved = dom_bytes / (stages[dom] * 1e-3) / 1e9
+        traffic, traffic_src = None, None
+        tp = os.path.join(ROOT, "profiles", "traffic.json")        # DRAM bytes per launch from the committed ncu capture
+        if os.path.exists(tp):
+            tj = json.load(open(tp))
+            key = dom + "_kernel"
+            if key in tj:
+                traffic, traffic_src = tj[key]["dram_bytes"], tj.get("_source")
         step_bytes = V * (52.0 * P + 40.0 * HW) + 76.0 * D + V * (60.0 * HW + 104.0 * P) + 76.0 * D
         cpu_v, cpu_n, cpu_dt = cpu_views_per_s(2, 10.0)
         dit_leg = None
@@ -347,7 +354,7 @@ def run_gpu(args):
                "data": "synthetic", "config": dict(CONFIG, instances_D=D),
                "wall_s_timed_region": wall, "stage_ms": stages,
                "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": hbm, "unit": "GB/s",
-                            "frac": achieved / hbm, "traffic": None, "peak_source": peak_src,
+                            "frac": achieved / hbm, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                             "algorithmic_bytes_per_launch": dom_bytes,
                             "whole_step_algorithmic_GBs": step_bytes / (dev_ms_max / args.steps * 1e-3) / 1e9},
                "cpu_baseline": {"value": cpu_v, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
