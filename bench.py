@@ -346,6 +346,7 @@ def run_gpu(args):
                     kk["frac_of_bf16_peak"] = kk["tflops"] / tpk
                 dit_leg["tensor_peak_tflops"] = tpk
                 dit_leg["frac_of_bf16_peak_sustained"] = dit_leg["tflops"] / float(pk.get("bf16_tflops_sustained", 1400.0))
+                dit_leg["deployed_L_N768"] = run_dit_deployed_leg(dev)
             except Exception as ex:                      # the raster metric is the headline; report, do not hide
                 dit_leg = {"error": repr(ex)}
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -455,6 +456,46 @@ def run_dit_leg(dev, steps_grid=50, reps=3):
             "e2e_samples_per_s": 1.0 / e2e_s, "launches_per_nfe": eng.launches_per_forward + 1,
             "kernels": {"self_attention": {"ms": 1e3 * t_attn, "tflops": fl_attn / t_attn / 1e12},
                         "gemm_mlp1_gelu": {"ms": 1e3 * t_gemm, "tflops": fl_gemm / t_gemm / 1e12}}}
+
+
+def run_dit_deployed_leg(dev, nfe=20):
+    """Deployed sizes: DiT-PixArt-PCD-CLAY-L (stage 1, C=3) and ...-stage2-L (C=10 + xyz PE),
+    L24 D1024 H16, N=768 latent points, M=1369 DINO tokens, CFG batch 2.  Reports ms per NFE of each stage and the
+    DiT part of the cascade at the reference's 250-point grids (2 x 249 NFE) derived from it."""
+    import torch
+    from gaussiananything_b200 import dit
+    torch.manual_seed(0)
+    N, M, Dc, B = 768, 1369, 1024, 2
+    out = {}
+    for name, cin, stage2 in (("DiT-PixArt-PCD-CLAY-L", 3, False), ("DiT-PixArt-PCD-CLAY-stage2-L", 10, True)):
+        m = dit.DiT_models[name](input_size=32, num_classes=0, learn_sigma=False, in_channels=cin, context_dim=Dc,
+                                 roll_out=True, pooling_ctx_dim=768)
+        m.randomize_zero_init_().to(dev)
+        z = torch.randn(B, N, cin, device=dev)
+        ctx = {"img_crossattn": torch.randn(B, M, Dc, device=dev), "img_vector": torch.randn(B, Dc, device=dev)}
+        if stage2:
+            ctx["fps-xyz"] = torch.rand(B, N, 3, device=dev) * 2 - 1
+        tt = torch.full((B,), 0.4, device=dev)
+        for _ in range(3):
+            y = m.forward_with_cfg(z, tt, ctx, 4.0)
+        assert torch.isfinite(y).all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(dev)
+        e0.record()
+        for _ in range(nfe):
+            m.forward_with_cfg(z, tt, ctx, 4.0)
+        e1.record()
+        e1.synchronize()
+        ms = e0.elapsed_time(e1) / nfe
+        fl = 2 * dit_flops_per_forward(24, N, 1024, M, Dc)
+        out[name] = {"ms_per_nfe": ms, "tflops": fl / (ms * 1e-3) / 1e12}
+        del m
+        torch.cuda.empty_cache()
+    tot = 249 * (out["DiT-PixArt-PCD-CLAY-L"]["ms_per_nfe"] + out["DiT-PixArt-PCD-CLAY-stage2-L"]["ms_per_nfe"]) * 1e-3
+    out["derived_cascade_dit_seconds_per_sample_2x249_nfe"] = tot
+    out["derived_dit_only_samples_per_s"] = 1.0 / tot
+    out["note"] = "DiT stages only (no DINOv2 conditioner, VAE decode or rendering: SURVEY 8f rows N1-N3 are not built yet)"
+    return out
 
 
 def main():

@@ -360,22 +360,24 @@ cudaError_t ga_launch_render_fwd(const RasterDims &d, const RasterWs &w, const f
 // This replaces a 32-lane reduction per (warp, surfel) hit -- where typically 8 of 32 lanes carried data --
 // by register accumulation over the pixels a surfel actually touches.
 // ---------------------------------------------------------------------------
-#define BWD_LIST_RECORDS 2048
+#define BWD_LIST_RECORDS 4096
+#define BWD_MAXG 128
 
 struct BwdSmem {
     float4 rec[6][CHUNK];
     uint4 list[BWD_LIST_RECORDS];
     float up[256][6];               // per pixel: dL/dcolor (3), dL/dnormal (3)
     uint32_t id[CHUNK];
-    int cnt[2][32];
+    int cnt[2][BWD_MAXG];
     int maxc;
 };
 
-// reduce-scatter of 18 components over TPI (8/16/32) consecutive lanes by recursive halving
+// reduce-scatter of 18 components over TPI (2/4/8/16) consecutive lanes by recursive halving: after level l a lane
+// is responsible for half of the components it held before; the fully reduced leftovers are added to dst.
 template <int TPI>
 __device__ __forceinline__ void reduce_scatter18(const float (&g)[GA_GRAD_F], int lane, float *__restrict__ dst)
 {
-    int off = 0, size = 18;
+    int off = 0, size = 9;
     float a9[10];
     {
         const bool u = lane & (TPI >> 1);
@@ -385,57 +387,60 @@ __device__ __forceinline__ void reduce_scatter18(const float (&g)[GA_GRAD_F], in
             a9[i] = keep + __shfl_xor_sync(0xffffffffu, send, TPI >> 1);
         }
         a9[9] = 0.f;
-        off += u ? 9 : 0; size = 9;
+        off += u ? 9 : 0;
     }
-    float b5[6];
-    {
-        const bool u = lane & (TPI >> 2);
+    if constexpr (TPI == 2) {
 #pragma unroll
-        for (int i = 0; i < 5; i++) {
-            const float keep = u ? a9[5 + i] : a9[i], send = u ? a9[i] : a9[5 + i];
-            b5[i] = keep + __shfl_xor_sync(0xffffffffu, send, TPI >> 2);
-        }
-        b5[5] = 0.f;
-        off += u ? 5 : 0; size = u ? 4 : 5;
-    }
-    float c3[4];
-    {
-        const bool u = lane & (TPI >> 3);
-#pragma unroll
-        for (int i = 0; i < 3; i++) {
-            const float keep = u ? b5[3 + i] : b5[i], send = u ? b5[i] : b5[3 + i];
-            c3[i] = keep + __shfl_xor_sync(0xffffffffu, send, TPI >> 3);
-        }
-        c3[3] = 0.f;
-        off += u ? 3 : 0; size = u ? size - 3 : 3;
-    }
-    if constexpr (TPI == 8) {
-#pragma unroll
-        for (int i = 0; i < 3; i++)
-            if (i < size && c3[i] != 0.f) atomicAdd(dst + off + i, c3[i]);
+        for (int i = 0; i < 9; i++)
+            if (a9[i] != 0.f) atomicAdd(dst + off + i, a9[i]);
         return;
     } else {
-        float d2[2];
+        float b5[6];
         {
-            const bool u = lane & (TPI >> 4);
+            const bool u = lane & (TPI >> 2);
 #pragma unroll
-            for (int i = 0; i < 2; i++) {
-                const float keep = u ? c3[2 + i] : c3[i], send = u ? c3[i] : c3[2 + i];
-                d2[i] = keep + __shfl_xor_sync(0xffffffffu, send, TPI >> 4);
+            for (int i = 0; i < 5; i++) {
+                const float keep = u ? a9[5 + i] : a9[i], send = u ? a9[i] : a9[5 + i];
+                b5[i] = keep + __shfl_xor_sync(0xffffffffu, send, TPI >> 2);
             }
-            off += u ? 2 : 0; size = u ? max(size - 2, 0) : min(size, 2);
+            b5[5] = 0.f;
+            off += u ? 5 : 0; size = u ? 4 : 5;
         }
-        if constexpr (TPI == 16) {
+        if constexpr (TPI == 4) {
 #pragma unroll
-            for (int i = 0; i < 2; i++)
-                if (i < size && d2[i] != 0.f) atomicAdd(dst + off + i, d2[i]);
+            for (int i = 0; i < 5; i++)
+                if (i < size && b5[i] != 0.f) atomicAdd(dst + off + i, b5[i]);
             return;
         } else {
-            const bool u = lane & 1;
-            const float keep = u ? d2[1] : d2[0], send = u ? d2[0] : d2[1];
-            const float e = keep + __shfl_xor_sync(0xffffffffu, send, 1);
-            off += u ? 1 : 0; size = u ? max(size - 1, 0) : min(size, 1);
-            if (size > 0 && e != 0.f) atomicAdd(dst + off, e);
+            float c3[4];
+            {
+                const bool u = lane & (TPI >> 3);
+#pragma unroll
+                for (int i = 0; i < 3; i++) {
+                    const float keep = u ? b5[3 + i] : b5[i], send = u ? b5[i] : b5[3 + i];
+                    c3[i] = keep + __shfl_xor_sync(0xffffffffu, send, TPI >> 3);
+                }
+                c3[3] = 0.f;
+                off += u ? 3 : 0; size = u ? size - 3 : 3;
+            }
+            if constexpr (TPI == 8) {
+#pragma unroll
+                for (int i = 0; i < 3; i++)
+                    if (i < size && c3[i] != 0.f) atomicAdd(dst + off + i, c3[i]);
+                return;
+            } else {
+                const bool u = lane & (TPI >> 4);
+                float d2[2];
+#pragma unroll
+                for (int i = 0; i < 2; i++) {
+                    const float keep = u ? c3[2 + i] : c3[i], send = u ? c3[i] : c3[2 + i];
+                    d2[i] = keep + __shfl_xor_sync(0xffffffffu, send, TPI >> 4);
+                }
+                off += u ? 2 : 0; size = u ? max(size - 2, 0) : min(size, 2);
+#pragma unroll
+                for (int i = 0; i < 2; i++)
+                    if (i < size && d2[i] != 0.f) atomicAdd(dst + off + i, d2[i]);
+            }
         }
     }
 }
@@ -553,7 +558,7 @@ render_bwd_kernel(RasterDims d, RasterWs ws, const float *__restrict__ bg,
 
     // nothing behind the deepest contributor of the tile can receive gradient
     if (threadIdx.x == 0) sm.maxc = 0;
-    if (threadIdx.x < 64) sm.cnt[threadIdx.x >> 5][threadIdx.x & 31] = 0;
+    sm.cnt[threadIdx.x >> 7][threadIdx.x & 127] = 0;
     __syncthreads();
     {
         int m = last_contributor;
@@ -569,7 +574,7 @@ render_bwd_kernel(RasterDims d, RasterWs ws, const float *__restrict__ bg,
         const int lo = max(0, hi - CHUNK);
         const int cnt = hi - lo;
         // stage positions lo..hi-1; slot t holds position hi-1-t (back to front)
-        int big64 = 0, big128 = 0;
+        int big32 = 0, big64 = 0, big128 = 0;
         if ((int)threadIdx.x < cnt) {
             const uint32_t id = ws.ids[start + (hi - 1 - threadIdx.x)];
             sm.id[threadIdx.x] = id;
@@ -582,88 +587,95 @@ render_bwd_kernel(RasterDims d, RasterWs ws, const float *__restrict__ bg,
             const float y0 = fmaxf(q[4].z, (float)oy), y1 = fminf(q[4].w, (float)(oy + 15));
             const int wx = max(0, (int)floorf(x1) - (int)ceilf(x0) + 1), wy = max(0, (int)floorf(y1) - (int)ceilf(y0) + 1);
             const int area = wx * wy;
-            big64 = area > 64; big128 = area > 128;
+            big32 = area > 32; big64 = area > 64; big128 = area > 128;
         }
+        const int any32 = __syncthreads_or(big32);
         const int any64 = __syncthreads_or(big64);
         const int any128 = __syncthreads_or(big128);
-        const int G = any128 ? 8 : (any64 ? 16 : 32);
+        // list capacity per surfel = 4096 / G must cover the pixels of its cull box inside the tile
+        const int G = any128 ? 16 : (any64 ? 32 : (any32 ? 64 : 128));
         const int cap = BWD_LIST_RECORDS / G;
 
         for (int g0 = 0; g0 < cnt; g0 += G, parity ^= 1) {
             const int gcnt = min(G, cnt - g0);
             int *cntp = sm.cnt[parity];
-            // ---------------- phase A
-            bool hit = false;
-            if (lane < gcnt) {
-                const float4 bb = sm.rec[4][g0 + lane];
-                hit = !(bb.y < bx_lo || bb.x > bx_hi || bb.w < by_lo || bb.z > by_hi);
-            }
-            unsigned mask = __ballot_sync(0xffffffffu, hit);
-            unsigned mine = 0;
-            while (mask) {
-                const int b = __ffs(mask) - 1;
-                mask &= mask - 1;
-                const float4 bb = sm.rec[4][g0 + b];
-                if (pfx >= bb.x && pfx <= bb.y && pfy >= bb.z && pfy <= bb.w && (hi - 1 - (g0 + b)) < last_contributor)
-                    mine |= 1u << b;
-            }
-            if (!inside) mine = 0;
-            while (__any_sync(0xffffffffu, mine != 0)) {
-                const bool active = mine != 0;
-                const int bsel = active ? __ffs(mine) - 1 : 0;
-                mine &= mine - 1;
-                const int jj = g0 + bsel;
-                const int contributor = hi - 1 - jj;       // 0-based list position
-                const float4 a = sm.rec[0][jj], b = sm.rec[1][jj], c = sm.rec[2][jj];
-                PixelGeom pg;
-                float k0, k1, k2, l0, l1, l2;
-                const bool ok = active && eval_pair(a, b, c, pfx, pfy, pg, k0, k1, k2, l0, l1, l2);
-                if (ok) {
-                    const float4 nr = sm.rec[3][jj], gb = sm.rec[5][jj];
-                    const float alpha = pg.alpha, c_d = pg.depth;
-                    const float inv1ma = fast_rcp(1.f - alpha);
-                    T = T * inv1ma;
-                    const float w = alpha * T;
-                    float dL_dalpha = 0.0f;
-                    ar0 = last_alpha * lc0 + (1.f - last_alpha) * ar0; lc0 = nr.w;
-                    ar1 = last_alpha * lc1 + (1.f - last_alpha) * ar1; lc1 = gb.x;
-                    ar2 = last_alpha * lc2 + (1.f - last_alpha) * ar2; lc2 = gb.y;
-                    dL_dalpha += (nr.w - ar0) * dpx0 + (gb.x - ar1) * dpx1 + (gb.y - ar2) * dpx2;
-                    float dL_dz = 0.0f;
-                    const float inv_cd = fast_rcp(c_d);
-                    const float m_d = GA_M_C0 - GA_M_C1 * inv_cd;
-                    const float dmd_dd = GA_M_C1 * inv_cd * inv_cd;
-                    if (contributor == median_contributor - 1) dL_dz += dL_dmedian;
-                    const float dL_dweight = (final_D2 + m_d * m_d * final_A - 2 * m_d * final_D) * dL_dreg;
-                    dL_dalpha += dL_dweight - last_dL_dT;
-                    last_dL_dT = dL_dweight * alpha + (1 - alpha) * last_dL_dT;
-                    const float dL_dmd = 2.0f * (T * alpha) * (m_d * final_A - final_D) * dL_dreg;
-                    dL_dz += dL_dmd * dmd_dd;
-                    accum_depth_rec = last_alpha * last_depth + (1.f - last_alpha) * accum_depth_rec;
-                    last_depth = c_d;
-                    dL_dalpha += (c_d - accum_depth_rec) * dL_ddepth;
-                    accum_alpha_rec = last_alpha + (1.f - last_alpha) * accum_alpha_rec;
-                    dL_dalpha += (1 - accum_alpha_rec) * dL_daccum;
-                    an0 = last_alpha * ln0 + (1.f - last_alpha) * an0; ln0 = nr.x;
-                    an1 = last_alpha * ln1 + (1.f - last_alpha) * an1; ln1 = nr.y;
-                    an2 = last_alpha * ln2 + (1.f - last_alpha) * an2; ln2 = nr.z;
-                    dL_dalpha += (nr.x - an0) * dn0 + (nr.y - an1) * dn1 + (nr.z - an2) * dn2;
-                    dL_dalpha *= T;
-                    last_alpha = alpha;
-                    dL_dalpha += (-T_final * inv1ma) * bg_dot_dpixel;
-                    dL_dz += w * dL_ddepth;
-                    const int slot = atomicAdd(&cntp[bsel], 1);
-                    if (slot < cap)
-                        sm.list[bsel * cap + slot] = make_uint4((uint32_t)pix_local, __float_as_uint(dL_dalpha),
-                                                                __float_as_uint(dL_dz), __float_as_uint(w));
+            // ---------------- phase A: sub-blocks of 32 surfels, no block barrier in between
+            for (int sb = 0; sb < gcnt; sb += 32) {
+                const int base = g0 + sb;
+                bool hit = false;
+                if (sb + lane < gcnt) {
+                    const float4 bb = sm.rec[4][base + lane];
+                    hit = !(bb.y < bx_lo || bb.x > bx_hi || bb.w < by_lo || bb.z > by_hi);
+                }
+                unsigned mask = __ballot_sync(0xffffffffu, hit);
+                unsigned mine = 0;
+                while (mask) {
+                    const int b = __ffs(mask) - 1;
+                    mask &= mask - 1;
+                    const float4 bb = sm.rec[4][base + b];
+                    if (pfx >= bb.x && pfx <= bb.y && pfy >= bb.z && pfy <= bb.w && (hi - 1 - (base + b)) < last_contributor)
+                        mine |= 1u << b;
+                }
+                if (!inside) mine = 0;
+                while (__any_sync(0xffffffffu, mine != 0)) {
+                    const bool active = mine != 0;
+                    const int bsel = active ? __ffs(mine) - 1 : 0;
+                    mine &= mine - 1;
+                    const int jj = base + bsel;
+                    const int contributor = hi - 1 - jj;       // 0-based list position
+                    const float4 a = sm.rec[0][jj], b = sm.rec[1][jj], c = sm.rec[2][jj];
+                    PixelGeom pg;
+                    float k0, k1, k2, l0, l1, l2;
+                    const bool ok = active && eval_pair(a, b, c, pfx, pfy, pg, k0, k1, k2, l0, l1, l2);
+                    if (ok) {
+                        const float4 nr = sm.rec[3][jj], gb = sm.rec[5][jj];
+                        const float alpha = pg.alpha, c_d = pg.depth;
+                        const float inv1ma = fast_rcp(1.f - alpha);
+                        T = T * inv1ma;
+                        const float w = alpha * T;
+                        float dL_dalpha = 0.0f;
+                        ar0 = last_alpha * lc0 + (1.f - last_alpha) * ar0; lc0 = nr.w;
+                        ar1 = last_alpha * lc1 + (1.f - last_alpha) * ar1; lc1 = gb.x;
+                        ar2 = last_alpha * lc2 + (1.f - last_alpha) * ar2; lc2 = gb.y;
+                        dL_dalpha += (nr.w - ar0) * dpx0 + (gb.x - ar1) * dpx1 + (gb.y - ar2) * dpx2;
+                        float dL_dz = 0.0f;
+                        const float inv_cd = fast_rcp(c_d);
+                        const float m_d = GA_M_C0 - GA_M_C1 * inv_cd;
+                        const float dmd_dd = GA_M_C1 * inv_cd * inv_cd;
+                        if (contributor == median_contributor - 1) dL_dz += dL_dmedian;
+                        const float dL_dweight = (final_D2 + m_d * m_d * final_A - 2 * m_d * final_D) * dL_dreg;
+                        dL_dalpha += dL_dweight - last_dL_dT;
+                        last_dL_dT = dL_dweight * alpha + (1 - alpha) * last_dL_dT;
+                        const float dL_dmd = 2.0f * (T * alpha) * (m_d * final_A - final_D) * dL_dreg;
+                        dL_dz += dL_dmd * dmd_dd;
+                        accum_depth_rec = last_alpha * last_depth + (1.f - last_alpha) * accum_depth_rec;
+                        last_depth = c_d;
+                        dL_dalpha += (c_d - accum_depth_rec) * dL_ddepth;
+                        accum_alpha_rec = last_alpha + (1.f - last_alpha) * accum_alpha_rec;
+                        dL_dalpha += (1 - accum_alpha_rec) * dL_daccum;
+                        an0 = last_alpha * ln0 + (1.f - last_alpha) * an0; ln0 = nr.x;
+                        an1 = last_alpha * ln1 + (1.f - last_alpha) * an1; ln1 = nr.y;
+                        an2 = last_alpha * ln2 + (1.f - last_alpha) * an2; ln2 = nr.z;
+                        dL_dalpha += (nr.x - an0) * dn0 + (nr.y - an1) * dn1 + (nr.z - an2) * dn2;
+                        dL_dalpha *= T;
+                        last_alpha = alpha;
+                        dL_dalpha += (-T_final * inv1ma) * bg_dot_dpixel;
+                        dL_dz += w * dL_ddepth;
+                        const int li = sb + bsel;                      // surfel index inside the group
+                        const int slot = atomicAdd(&cntp[li], 1);
+                        if (slot < cap)
+                            sm.list[li * cap + slot] = make_uint4((uint32_t)pix_local, __float_as_uint(dL_dalpha),
+                                                                  __float_as_uint(dL_dz), __float_as_uint(w));
+                    }
                 }
             }
             __syncthreads();
             // ---------------- phase B
-            if (threadIdx.x < 32) sm.cnt[parity ^ 1][threadIdx.x] = 0;      // counters of the next group
-            if (G == 32) bwd_phase_b<8>(sm, cntp, g0, gcnt, cap, ox, oy, acc_base);
-            else if (G == 16) bwd_phase_b<16>(sm, cntp, g0, gcnt, cap, ox, oy, acc_base);
-            else bwd_phase_b<32>(sm, cntp, g0, gcnt, cap, ox, oy, acc_base);
+            if (threadIdx.x < BWD_MAXG) sm.cnt[parity ^ 1][threadIdx.x] = 0;      // counters of the next group
+            if (G == 128) bwd_phase_b<2>(sm, cntp, g0, gcnt, cap, ox, oy, acc_base);
+            else if (G == 64) bwd_phase_b<4>(sm, cntp, g0, gcnt, cap, ox, oy, acc_base);
+            else if (G == 32) bwd_phase_b<8>(sm, cntp, g0, gcnt, cap, ox, oy, acc_base);
+            else bwd_phase_b<16>(sm, cntp, g0, gcnt, cap, ox, oy, acc_base);
             __syncthreads();
         }
     }
