@@ -87,12 +87,12 @@ static void carve(const GaRasterLayout &L, void *base, RasterWs *w)
     w->n_contrib = (int32_t *)(p + L.n_contrib);
 }
 
-extern "C" int ga_raster_forward(const float *gauss13, int batch, int P, int views,
-                                 const float *viewmats, const float *projmats, const float *bg,
-                                 int H, int W, float scale_modifier,
-                                 float *out_color, float *out_allmap, int32_t *out_radii,
-                                 void *workspace, size_t workspace_bytes, int64_t max_instances,
-                                 void *stream)
+static int raster_forward_impl(int stage, const float *gauss13, int batch, int P, int views,
+                               const float *viewmats, const float *projmats, const float *bg,
+                               int H, int W, float scale_modifier,
+                               float *out_color, float *out_allmap, int32_t *out_radii,
+                               void *workspace, size_t workspace_bytes, int64_t max_instances,
+                               void *stream)
 {
     RasterDims d;
     int rc = make_dims(batch, P, views, H, W, scale_modifier, max_instances, &d);
@@ -106,16 +106,53 @@ extern "C" int ga_raster_forward(const float *gauss13, int batch, int P, int vie
     carve(L, workspace, &w);
     cudaStream_t s = (cudaStream_t)stream;
     cudaError_t e;
-    if ((e = cudaMemsetAsync(w.status, 0, 16 * sizeof(int32_t), s)) != cudaSuccess) return (int)e;
-    if ((e = cudaMemsetAsync(w.tile_count, 0, (size_t)d.NV * d.T * sizeof(uint32_t), s)) != cudaSuccess) return (int)e;
-    prof(0, s);
-    if ((e = ga_launch_preprocess(d, w, gauss13, viewmats, projmats, out_radii, s)) != cudaSuccess) return (int)e;
-    prof(1, s);
-    if ((e = ga_launch_binning(d, w, s)) != cudaSuccess) return (int)e;
-    prof(2, s);
-    if ((e = ga_launch_render_fwd(d, w, bg, out_color, out_allmap, s)) != cudaSuccess) return (int)e;
-    prof(3, s);
+    if (stage == 0 || stage == 1) {
+        if ((e = cudaMemsetAsync(w.status, 0, 16 * sizeof(int32_t), s)) != cudaSuccess) return (int)e;
+        if ((e = cudaMemsetAsync(w.tile_count, 0, (size_t)d.NV * d.T * sizeof(uint32_t), s)) != cudaSuccess) return (int)e;
+        prof(0, s);
+        if ((e = ga_launch_preprocess(d, w, gauss13, viewmats, projmats, out_radii, s)) != cudaSuccess) return (int)e;
+        prof(1, s);
+        if ((e = ga_launch_binning(d, w, s)) != cudaSuccess) return (int)e;
+        prof(2, s);
+    }
+    if (stage == 0 || stage == 2) {
+        if ((e = ga_launch_render_fwd(d, w, bg, out_color, out_allmap, s)) != cudaSuccess) return (int)e;
+        prof(3, s);
+    }
     return 0;
+}
+
+extern "C" int ga_raster_forward(const float *gauss13, int batch, int P, int views,
+                                 const float *viewmats, const float *projmats, const float *bg,
+                                 int H, int W, float scale_modifier,
+                                 float *out_color, float *out_allmap, int32_t *out_radii,
+                                 void *workspace, size_t workspace_bytes, int64_t max_instances,
+                                 void *stream)
+{
+    return raster_forward_impl(0, gauss13, batch, P, views, viewmats, projmats, bg, H, W, scale_modifier, out_color,
+                               out_allmap, out_radii, workspace, workspace_bytes, max_instances, stream);
+}
+
+extern "C" int ga_raster_forward_bin(const float *gauss13, int batch, int P, int views,
+                                     const float *viewmats, const float *projmats, const float *bg,
+                                     int H, int W, float scale_modifier,
+                                     float *out_color, float *out_allmap, int32_t *out_radii,
+                                     void *workspace, size_t workspace_bytes, int64_t max_instances,
+                                     void *stream)
+{
+    return raster_forward_impl(1, gauss13, batch, P, views, viewmats, projmats, bg, H, W, scale_modifier, out_color,
+                               out_allmap, out_radii, workspace, workspace_bytes, max_instances, stream);
+}
+
+extern "C" int ga_raster_forward_render(const float *gauss13, int batch, int P, int views,
+                                        const float *viewmats, const float *projmats, const float *bg,
+                                        int H, int W, float scale_modifier,
+                                        float *out_color, float *out_allmap, int32_t *out_radii,
+                                        void *workspace, size_t workspace_bytes, int64_t max_instances,
+                                        void *stream)
+{
+    return raster_forward_impl(2, gauss13, batch, P, views, viewmats, projmats, bg, H, W, scale_modifier, out_color,
+                               out_allmap, out_radii, workspace, workspace_bytes, max_instances, stream);
 }
 
 extern "C" size_t ga_raster_backward_scratch_bytes(int batch, int P, int views)

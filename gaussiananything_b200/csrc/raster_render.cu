@@ -915,7 +915,7 @@ cudaError_t ga_launch_render_bwd(const RasterDims &d, const RasterWs &w, const f
     }
     dim3 grid(d.gx, d.gy, d.NV);
     static int variant = -1;
-    if (variant < 0) { const char *e = getenv("GA_B200_BWD"); variant = (e && e[0] == '3') ? 3 : 2; }
+    if (variant < 0) { const char *e = getenv("GA_B200_BWD"); variant = (e && e[0] == '2') ? 2 : 3; }   // default: two-phase
     if (variant == 3) render_bwd_kernel<<<grid, 256, sizeof(BwdSmem), s>>>(d, w, bg, dL_dcolor, dL_dallmap, grad_acc);
     else render_bwd_kernel_v2<<<grid, 256, 0, s>>>(d, w, bg, dL_dcolor, dL_dallmap, grad_acc);
     return cudaGetLastError();

@@ -72,12 +72,14 @@ def forward_raw(gauss13, viewmats, projmats, bg, H, W, scale_modifier=1.0, max_i
     while True:
         L = layout(B, P, V, H, W, max_instances)
         ws = torch.empty(L.total_bytes, device=dev, dtype=torch.uint8)
-        rc = lib.ga_raster_forward(_ptr(gauss13), B, P, V, _ptr(viewmats), _ptr(projmats), _ptr(bg),
-                                   H, W, float(scale_modifier), _ptr(color), _ptr(allmap), _ptr(radii),
-                                   _ptr(ws), L.total_bytes, max_instances, _stream(dev))
-        _lib.check(rc, "ga_raster_forward")
-        status = ws[L.status:L.status + 64].view(torch.int32).cpu()   # one sync per call
+        args = (_ptr(gauss13), B, P, V, _ptr(viewmats), _ptr(projmats), _ptr(bg), H, W, float(scale_modifier),
+                _ptr(color), _ptr(allmap), _ptr(radii), _ptr(ws), L.total_bytes, max_instances, _stream(dev))
+        _lib.check(lib.ga_raster_forward_bin(*args), "ga_raster_forward_bin")
+        # one small device->host read after the binning (where upstream reads num_rendered back); the composite is
+        # enqueued afterwards, so the GPU keeps working while the host goes on to enqueue whatever follows
+        status = ws[L.status:L.status + 64].view(torch.int32).cpu()
         if int(status[1]) == 0:
+            _lib.check(lib.ga_raster_forward_render(*args), "ga_raster_forward_render")
             break
         max_instances = int(int(status[0]) * 1.25) + 1024
         _capacity_hint[key] = max_instances

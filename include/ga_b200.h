@@ -74,6 +74,20 @@ int ga_raster_forward(const float *gauss13, int batch, int P, int views,
                       void *workspace, size_t workspace_bytes, int64_t max_instances,
                       void *stream);
 
+/* The same forward in two halves, for callers that want to look at status[0..1] (instance count, overflow) after
+ * the binning -- the point where upstream reads `num_rendered` back (rasterizer_impl.cu) -- and only then enqueue
+ * the composite: ga_raster_forward_bin = per-surfel stage + binning, ga_raster_forward_render = composite. */
+int ga_raster_forward_bin(const float *gauss13, int batch, int P, int views,
+                          const float *viewmats, const float *projmats, const float *bg,
+                          int H, int W, float scale_modifier,
+                          float *out_color, float *out_allmap, int32_t *out_radii,
+                          void *workspace, size_t workspace_bytes, int64_t max_instances, void *stream);
+int ga_raster_forward_render(const float *gauss13, int batch, int P, int views,
+                             const float *viewmats, const float *projmats, const float *bg,
+                             int H, int W, float scale_modifier,
+                             float *out_color, float *out_allmap, int32_t *out_radii,
+                             void *workspace, size_t workspace_bytes, int64_t max_instances, void *stream);
+
 /* Bytes of scratch the backward needs (gradient accumulators). */
 size_t ga_raster_backward_scratch_bytes(int batch, int P, int views);
 
