@@ -110,6 +110,7 @@ class ClockSampler:
 def cpu_views_per_s(n_views, min_seconds, seed=40):
     from oracle import surfel_oracle as so
     from tests.helpers import oracle_view
+    so.set_num_threads(os.cpu_count() or 1)            # torchrun exports OMP_NUM_THREADS=1
     g, vs, ps = make_inputs(seed)
     rng = np.random.default_rng(0)
     gc = rng.standard_normal((3, RES, RES)).astype(np.float32)
@@ -335,7 +336,7 @@ def run_gpu(args):
             if key in tj:
                 traffic, traffic_src = tj[key]["dram_bytes"], tj.get("_source")
         step_bytes = V * (52.0 * P + 40.0 * HW) + 76.0 * D + V * (60.0 * HW + 104.0 * P) + 76.0 * D
-        cpu_v, cpu_n, cpu_dt = cpu_views_per_s(2, 10.0)
+        cpu_v, cpu_n, cpu_dt = cpu_views_per_s(2, 10.0) if world == 1 else (None, 0, 0.0)
         dit_leg = None
         if world == 1 and not args.no_dit:
             try:
@@ -358,9 +359,10 @@ def run_gpu(args):
                             "frac": achieved / hbm, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                             "algorithmic_bytes_per_launch": dom_bytes,
                             "whole_step_algorithmic_GBs": step_bytes / (dev_ms_max / args.steps * 1e-3) / 1e9},
-               "cpu_baseline": {"value": cpu_v, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
-                                "sample": "%d views fwd+bwd of the same 100k/512^2 scene in %.1f s "
-                                          "(oracle/surfel_oracle.c, OpenMP)" % (cpu_n, cpu_dt)},
+               "cpu_baseline": ({"value": cpu_v, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                                 "sample": "%d views fwd+bwd of the same 100k/512^2 scene in %.1f s "
+                                           "(oracle/surfel_oracle.c, OpenMP)" % (cpu_n, cpu_dt)}
+                                if world == 1 else None),
                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
                "gpu_launches": 7 * args.steps, "clocks": clocks, "dit": dit_leg}
         print(json.dumps(out))

@@ -44,6 +44,10 @@ def lib():
     L.ga_raster_backward.argtypes = [vp, i32, i32, i32, vp, vp, vp, i32, i32, f32,
                                      vp, vp, vp, vp, sz, i64, vp, sz, vp, vp]
     L.ga_raster_backward.restype = i32
+    L.ga_render_post_forward.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp, vp, vp, vp, vp]
+    L.ga_render_post_forward.restype = i32
+    L.ga_render_post_backward.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.ga_render_post_backward.restype = i32
     L.ga_b200_version.restype = C.c_char_p
     _lib = L
     return L

@@ -35,15 +35,9 @@ class GaussianRenderer2DGS:
         color, allmap, _radii = _raster.rasterize_surfels_batched(
             gaussians, cam_view, cam_view_proj.float(), bg_color, int(output_size), int(output_size),
             float(scale_modifier))
-        alphas = allmap[:, :, 1:2]
-        # normals: camera -> world, (n^T @ view[:3,:3].T) per pixel (reference :125-128)
-        R = cam_view[:, :, :3, :3]
-        n = allmap[:, :, 2:5]
-        normals = torch.stack([n[:, :, 0] * R[:, :, d, 0, None, None] + n[:, :, 1] * R[:, :, d, 1, None, None]
-                               + n[:, :, 2] * R[:, :, d, 2, None, None] for d in range(3)], dim=2)
-        depths = torch.nan_to_num(allmap[:, :, 5:6], 0, 0)        # median depth, depth_ratio = 1
-        dists = allmap[:, :, 6:7]
-        images = color.clamp(0, 1)
+        # alpha / camera->world normals / nan-safe median depth / distortion / clamped image (reference :121-163),
+        # one fused kernel for all views instead of ~10 torch kernels per view
+        images, alphas, depths, normals, dists = _raster.render_postprocess(color, allmap, cam_view)
         return {
             "image": images,            # [B, V, 3, H, W]
             "alpha": alphas,            # [B, V, 1, H, W]

@@ -126,3 +126,44 @@ def rasterize_surfels_batched(gauss13, viewmats, projmats, bg, H, W, scale_modif
     """Differentiable batched rasterisation (grad w.r.t. gauss13 only, like the
     reference, whose cameras and background carry no gradient)."""
     return _RasterizeSurfelsBatched.apply(gauss13, viewmats, projmats, bg, H, W, scale_modifier)
+
+
+class _RenderPost(torch.autograd.Function):
+    """Fused per-view post-processing (reference nsr/gs_surfel.py:121-163) with its own backward kernel."""
+
+    @staticmethod
+    def forward(ctx, color, allmap, viewmats):
+        lib = _lib.lib()
+        B, V, _, H, W = color.shape
+        dev = color.device
+        color, allmap = color.contiguous(), allmap.contiguous()
+        vm = viewmats.reshape(B * V, 16).contiguous().float()
+        image = torch.empty(B, V, 3, H, W, device=dev)
+        alpha = torch.empty(B, V, 1, H, W, device=dev)
+        depth = torch.empty(B, V, 1, H, W, device=dev)
+        normal = torch.empty(B, V, 3, H, W, device=dev)
+        dist = torch.empty(B, V, 1, H, W, device=dev)
+        _lib.check(lib.ga_render_post_forward(_ptr(color), _ptr(allmap), _ptr(vm), B * V, H, W, _ptr(image), _ptr(alpha),
+                                              _ptr(depth), _ptr(normal), _ptr(dist), _stream(dev)), "ga_render_post_forward")
+        ctx.save_for_backward(color, allmap, vm)
+        return image, alpha, depth, normal, dist
+
+    @staticmethod
+    def backward(ctx, g_image, g_alpha, g_depth, g_normal, g_dist):
+        lib = _lib.lib()
+        color, allmap, vm = ctx.saved_tensors
+        B, V, _, H, W = color.shape
+        dev = color.device
+        gs = [None if g is None else g.contiguous().float() for g in (g_image, g_alpha, g_depth, g_normal, g_dist)]
+        g_color = torch.empty_like(color)
+        g_allmap = torch.empty_like(allmap)
+        null = C.c_void_p(0)
+        ptrs = [null if g is None else _ptr(g) for g in gs]
+        _lib.check(lib.ga_render_post_backward(_ptr(color), _ptr(allmap), _ptr(vm), B * V, H, W, *ptrs, _ptr(g_color),
+                                               _ptr(g_allmap), _stream(dev)), "ga_render_post_backward")
+        return g_color, g_allmap, None
+
+
+def render_postprocess(color, allmap, viewmats):
+    """(image, alpha, depth, rend_normal, dist) from the raw rasteriser outputs, differentiable."""
+    return _RenderPost.apply(color, allmap, viewmats)

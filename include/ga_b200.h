@@ -88,6 +88,17 @@ int ga_raster_forward_render(const float *gauss13, int batch, int P, int views,
                              float *out_color, float *out_allmap, int32_t *out_radii,
                              void *workspace, size_t workspace_bytes, int64_t max_instances, void *stream);
 
+/* Post-processing of /root/reference/nsr/gs_surfel.py:121-163 for all views at once: image = clamp(color,0,1),
+ * alpha = allmap[1], depth = nan_to_num(allmap[5], 0, 0), normal[d] = sum_c allmap[2+c] * view[d][c], dist = allmap[6].
+ * color [NV,3,H,W], allmap [NV,7,H,W], viewmats [NV,16] (as passed to the rasteriser); outputs contiguous. */
+int ga_render_post_forward(const float *color, const float *allmap, const float *viewmats, int num_views,
+                           int H, int W, float *image, float *alpha, float *depth, float *normal, float *dist,
+                           void *stream);
+/* Its backward: any g_* may be NULL (= zero); writes g_color [NV,3,H,W] and g_allmap [NV,7,H,W]. */
+int ga_render_post_backward(const float *color, const float *allmap, const float *viewmats, int num_views,
+                            int H, int W, const float *g_image, const float *g_alpha, const float *g_depth,
+                            const float *g_normal, const float *g_dist, float *g_color, float *g_allmap, void *stream);
+
 /* Bytes of scratch the backward needs (gradient accumulators). */
 size_t ga_raster_backward_scratch_bytes(int batch, int P, int views);
 

@@ -34,6 +34,22 @@
 #include <stdlib.h>
 #include <string.h>
 
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+/* Launchers such as torchrun export OMP_NUM_THREADS=1; the CPU baseline wants every host core. */
+int so_set_num_threads(int n)
+{
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+    return omp_get_max_threads();
+#else
+    (void)n;
+    return 1;
+#endif
+}
+
 #define BLOCK_X 16
 #define BLOCK_Y 16
 #define NEAR_N 0.2f

@@ -28,6 +28,13 @@ def lib():
     return _LIB
 
 
+def set_num_threads(n):
+    """Number of OpenMP threads the C oracle uses from now on (returns what is in effect)."""
+    L = lib()
+    L.so_set_num_threads.restype = C.c_int
+    return int(L.so_set_num_threads(C.c_int(int(n))))
+
+
 def _p(a, t):
     return a.ctypes.data_as(C.POINTER(t))
 

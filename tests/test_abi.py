@@ -63,3 +63,24 @@ def test_cpu_tensors_fail_loudly():
     with pytest.raises(RuntimeError):
         raster.forward_raw(torch.zeros(1, 4, 13), torch.eye(4).reshape(1, 1, 4, 4),
                            torch.eye(4).reshape(1, 1, 4, 4), torch.ones(3), 32, 32)
+
+
+def test_install_shims_registers_reference_module_names():
+    import sys
+    import gaussiananything_b200 as ga
+    saved = {k: sys.modules.get(k) for k in ("diff_surfel_rasterization", "transport", "transport.transport")}
+    try:
+        ga.install_shims()
+        import diff_surfel_rasterization as dsr          # the name nsr/gs_surfel.py:15 imports
+        import transport as tr                           # the name flow_matching_trainer.py imports
+        assert hasattr(dsr, "GaussianRasterizationSettings") and hasattr(dsr, "GaussianRasterizer")
+        assert hasattr(tr, "create_transport") and hasattr(tr, "Sampler")
+        fields = dsr.GaussianRasterizationSettings._fields
+        assert fields == ("image_height", "image_width", "tanfovx", "tanfovy", "bg", "scale_modifier", "viewmatrix",
+                          "projmatrix", "sh_degree", "campos", "prefiltered", "debug")
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v

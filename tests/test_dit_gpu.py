@@ -124,6 +124,24 @@ def test_attention(B, H, Nq, Nk, static_bound):
     assert rel(out.float(), ref) < 6e-3, rel(out.float(), ref)
 
 
+def test_attention_bound_too_large_falls_back_to_online_softmax():
+    """score_bound > 40 (or <= 0) must take the running-maximum path: large logits stay exact."""
+    dit, L, dev, st = _env()
+    torch.manual_seed(5)
+    B, H, N = 1, 2, 256
+    q = (torch.randn(B * H, N, 64, device=dev) * 4.0).bfloat16()
+    k = (torch.randn(B * H, N, 64, device=dev) * 4.0).bfloat16()
+    vt = torch.randn(B * H, 64, N, device=dev).bfloat16()
+    ref = torch.nn.functional.scaled_dot_product_attention(
+        q.float().view(B, H, N, 64), k.float().view(B, H, N, 64), vt.float().transpose(-1, -2).reshape(B, H, N, 64))
+    ref = ref.transpose(1, 2).reshape(B, N, H * 64)
+    for bound in (0.0, 500.0):
+        out = torch.zeros(B, N, H * 64, device=dev, dtype=torch.bfloat16)
+        assert L.ga_attention_bf16(dit._p(q), dit._p(k), dit._p(vt), dit._p(out), B, H, N, N, N, N, 0.125, bound, st) == 0
+        torch.cuda.synchronize()
+        assert rel(out.float(), ref) < 8e-3, (bound, rel(out.float(), ref))
+
+
 def test_row_kernels():
     dit, L, dev, st = _env()
     torch.manual_seed(1)

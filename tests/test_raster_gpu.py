@@ -270,3 +270,38 @@ def test_full_size_properties():
     ga = raster.backward_raw(s1, g1, g2)
     gb = raster.backward_raw(s1, 2.0 * g1, 2.0 * g2)
     assert rel_l2(gb.cpu().numpy(), 2.0 * ga.cpu().numpy()) <= 1e-4
+
+
+def test_fused_postprocess_matches_reference_formulas_and_autograd():
+    """render_postprocess == the torch ops of /root/reference/nsr/gs_surfel.py:121-163, forward and backward."""
+    from gaussiananything_b200 import raster
+    dev = torch.device("cuda:0")
+    torch.manual_seed(3)
+    B, V, H, W = 2, 3, 40, 56
+    color = (torch.rand(B, V, 3, H, W, device=dev) * 1.4 - 0.2).requires_grad_(True)       # some values outside [0,1]
+    allmap = torch.randn(B, V, 7, H, W, device=dev)
+    allmap[0, 0, 5, 0, :5] = float("nan")
+    allmap[0, 1, 5, 1, :5] = float("inf")
+    allmap = allmap.requires_grad_(True)
+    cam = torch.randn(B, V, 4, 4, device=dev)
+    outs = raster.render_postprocess(color, allmap, cam)
+    ws = [torch.randn_like(o) for o in outs]
+    (sum((o * w).sum() for o, w in zip(outs, ws))).backward()
+    g_color, g_allmap = color.grad.clone(), allmap.grad.clone()
+    color.grad = None; allmap.grad = None
+    # reference formulas (per view in the reference, batched here)
+    image = color.clamp(0, 1)
+    alpha = allmap[:, :, 1:2]
+    normal = (allmap[:, :, 2:5].permute(0, 1, 3, 4, 2) @ cam[:, :, None, :3, :3].transpose(-1, -2)).permute(0, 1, 4, 2, 3)
+    depth = torch.nan_to_num(allmap[:, :, 5:6], 0, 0)
+    dist = allmap[:, :, 6:7]
+    refs = (image, alpha, depth, normal, dist)
+    for o, r in zip(outs, refs):
+        assert o.shape == r.shape and torch.allclose(o, r, atol=1e-5, rtol=1e-5)
+    (sum((r * w).sum() for r, w in zip(refs, ws))).backward()
+    assert torch.allclose(g_color, color.grad, atol=1e-5)
+    fin = torch.isfinite(allmap.detach()[:, :, 5])
+    ga_ref = allmap.grad.clone()
+    ga_ref[:, :, 5][~fin] = 0.0                      # torch propagates a gradient through nan_to_num; the value is unused
+    g_allmap[:, :, 5][~fin] = 0.0
+    assert torch.allclose(g_allmap, ga_ref, atol=1e-4, rtol=1e-4)
