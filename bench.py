@@ -364,7 +364,7 @@ def run_gpu(args):
                                            "(oracle/surfel_oracle.c, OpenMP)" % (cpu_n, cpu_dt)}
                                 if world == 1 else None),
                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-               "gpu_launches": 7 * args.steps, "clocks": clocks, "dit": dit_leg}
+               "gpu_launches": 8 * args.steps, "clocks": clocks, "dit": dit_leg}
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
