@@ -193,32 +193,36 @@ sort_tiles_warp_kernel(RasterDims d, RasterWs ws)
     else warp_sort_tile<16>(gk, gid, n, lane);
 }
 
+// tiles with more than SORT_WARP_MAX instances: one block per tile, a small persistent grid walks all tiles
 __global__ void __launch_bounds__(256)
 sort_tiles_kernel(RasterDims d, RasterWs ws)
 {
     __shared__ unsigned long long s_keys[SORT_SMEM_KEYS];
     if (ws.status[1]) return;
-    const size_t t = blockIdx.x;
-    const uint32_t start = ws.tile_start[t], end = ws.tile_start[t + 1];
-    const int n = (int)(end - start);
-    if (n <= SORT_WARP_MAX) return;                 // done by sort_tiles_warp_kernel
-    unsigned long long *gk = ws.keys + start;
-    if (n <= SORT_SMEM_KEYS) {
-        for (int i = threadIdx.x; i < n; i += blockDim.x) s_keys[i] = gk[i];
-        __syncthreads();
-        block_bitonic_sort(s_keys, n);
-        for (int i = threadIdx.x; i < n; i += blockDim.x) {
-            const unsigned long long k = s_keys[i];
-            gk[i] = k;
-            ws.ids[start + i] = (uint32_t)(k & 0xffffffffull);
+    const size_t tiles = (size_t)d.NV * d.T;
+    for (size_t t = blockIdx.x; t < tiles; t += gridDim.x) {
+        const uint32_t start = ws.tile_start[t], end = ws.tile_start[t + 1];
+        const int n = (int)(end - start);
+        if (n <= SORT_WARP_MAX) continue;               // done by sort_tiles_warp_kernel (block-uniform branch)
+        unsigned long long *gk = ws.keys + start;
+        if (n <= SORT_SMEM_KEYS) {
+            for (int i = threadIdx.x; i < n; i += blockDim.x) s_keys[i] = gk[i];
+            __syncthreads();
+            block_bitonic_sort(s_keys, n);
+            for (int i = threadIdx.x; i < n; i += blockDim.x) {
+                const unsigned long long k = s_keys[i];
+                gk[i] = k;
+                ws.ids[start + i] = (uint32_t)(k & 0xffffffffull);
+            }
+            __syncthreads();                            // s_keys is reused by the next tile
+        } else {
+            // rare: a tile with more instances than fit in shared memory is sorted
+            // in place in global memory (L2 resident) by the same network.
+            if (threadIdx.x == 0) atomicAdd(&ws.status[2], 1);
+            block_bitonic_sort(gk, n);
+            for (int i = threadIdx.x; i < n; i += blockDim.x)
+                ws.ids[start + i] = (uint32_t)(gk[i] & 0xffffffffull);
         }
-    } else {
-        // rare: a tile with more instances than fit in shared memory is sorted
-        // in place in global memory (L2 resident) by the same network.
-        if (threadIdx.x == 0) atomicAdd(&ws.status[2], 1);
-        block_bitonic_sort(gk, n);
-        for (int i = threadIdx.x; i < n; i += blockDim.x)
-            ws.ids[start + i] = (uint32_t)(gk[i] & 0xffffffffull);
     }
 }
 
@@ -228,6 +232,7 @@ cudaError_t ga_launch_binning(const RasterDims &d, const RasterWs &w, cudaStream
     dim3 grid((d.P + 255) / 256, d.NV);
     scatter_kernel<<<grid, 256, 0, s>>>(d, w);
     sort_tiles_warp_kernel<<<(d.NV * d.T + 7) / 8, 256, 0, s>>>(d, w);
-    sort_tiles_kernel<<<d.NV * d.T, 256, 0, s>>>(d, w);
+    const int big_grid = d.NV * d.T < 592 ? d.NV * d.T : 592;
+    sort_tiles_kernel<<<big_grid, 256, 0, s>>>(d, w);
     return cudaGetLastError();
 }

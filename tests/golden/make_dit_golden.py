@@ -180,3 +180,6 @@ run("dit_stage1_small", dit_i23d.DiT_I23D_PCD_PixelArt_noclip, 1, B=1, N=24, M=1
     depth=2, hidden_size=128, num_heads=2)
 run("dit_stage2_small", dit_i23d.DiT_I23D_PCD_PixelArt_noclip_clay_stage2, 2, B=1, N=16, M=7, Cin=10, ctx_dim=32,
     stage2=True, depth=1, hidden_size=64, num_heads=1, use_pe_cond=True)
+# stage 2 in concatenation mode (x_embedder sees cat([fps_xyz, x]); the stage2-B registry entry uses it)
+run("dit_stage2_concat_small", dit_i23d.DiT_I23D_PCD_PixelArt_noclip_clay_stage2, 3, B=2, N=20, M=9, Cin=10, ctx_dim=32,
+    stage2=True, depth=1, hidden_size=64, num_heads=1, use_pe_cond=False)

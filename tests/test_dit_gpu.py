@@ -189,7 +189,7 @@ def _build(g, dev):
     return m.to(dev)
 
 
-@pytest.mark.parametrize("name", ["dit_stage1_small", "dit_stage2_small"])
+@pytest.mark.parametrize("name", ["dit_stage1_small", "dit_stage2_small", "dit_stage2_concat_small"])
 def test_dit_forward_matches_oracle_and_reference_golden(name):
     from oracle import dit_oracle as do
     g = do.load_golden(os.path.join(GOLD, name + ".npz"))

@@ -8,7 +8,7 @@ import torch
 from oracle import dit_oracle as do
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-NAMES = ["dit_stage1_small", "dit_stage2_small"]
+NAMES = ["dit_stage1_small", "dit_stage2_small", "dit_stage2_concat_small"]
 
 
 def rel(a, b):
