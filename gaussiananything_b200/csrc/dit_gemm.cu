@@ -23,10 +23,11 @@ constexpr int kEpiWarps = 8;
 constexpr int kThreads = 64 + 32 * kEpiWarps;          // TMA warp + MMA warp + 8 epilogue warps
 
 template <int BN> struct GemmCfg {
-    static constexpr int kStages = (BN >= 256) ? 4 : 6;
+    static constexpr int kStages = (BN >= 256) ? 3 : (BN >= 128 ? 5 : 7);      // + 36 KB of epilogue staging
     static constexpr int kABytes = BM * BK * 2;
     static constexpr int kBBytes = BN * BK * 2;
-    static constexpr int kSmem = kStages * (kABytes + kBBytes) + 1024;
+    static constexpr int kRing = kStages * (kABytes + kBBytes);
+    static constexpr int kSmem = kRing + 1024 + 36 * 1024;
     static constexpr int kTmemCols = 2 * BN;           // double-buffered accumulator
 };
 
@@ -55,80 +56,147 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b)
     return *reinterpret_cast<uint32_t *>(&h);
 }
 
-// epilogue for 32 consecutive columns [n, n+32) of one row (v[] = accumulator + bias already added)
-__device__ __forceinline__ void epilogue32(const GaGemmEpilogue &ep, int m, int n, int N, float (&v)[32])
+// ---- epilogue ---------------------------------------------------------------
+// tcgen05.ld hands every thread ONE accumulator row, so storing straight from that layout makes each warp store
+// touch 32 different rows (32 sectors per instruction) -- measured, the store queue then bounds the whole GEMM
+// (epilogue warps busy ~90 % of the time, tensor pipe ~30 %).  Each epilogue warp therefore owns a 4 KB staging
+// buffer (32 rows x 128 B, 16-byte chunks XOR-swizzled by row&7 so both phases are bank-conflict free):
+//   phase A (thread = row)          : TMEM -> registers -> staging
+//   phase B (8 lanes = one 128 B row): staging -> bias / GELU / gate / residual -> coalesced global stores
+// The epilogue mode is a template parameter: with a run-time switch inside the unrolled loops the kernel grew to
+// 5k instructions and a fifth of the epilogue's stall samples were instruction-cache misses.
+constexpr int kStageBytes = 4096;          // per epilogue warp
+constexpr int kHeadParams = 128;           // floats per epilogue warp: 64 bias + 64 norm weights (HEADS mode)
+
+// explicit shared-space accesses: through generic pointers the compiler could not prove that the staging loads
+// do not alias the global stores and serialised phase B load -> store -> load ...
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d)
 {
-    const bool full = (n + 32 <= N);
-    switch (ep.mode) {
-    case GA_EPI_BF16:
-    case GA_EPI_GELU_BF16: {
-        if (ep.mode == GA_EPI_GELU_BF16) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d));
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr)
+{
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];\n" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void warp_sync_smem() { asm volatile("bar.warp.sync 0xffffffff;\n" ::: "memory"); }
+
+__device__ __forceinline__ void stage_rows(uint32_t stg, int lane, const uint32_t (&r)[32])
+{
+    const uint32_t row = stg + lane * 128;
 #pragma unroll
-            for (int i = 0; i < 32; i++) v[i] = gelu_erf(v[i]);
-        }
-        __nv_bfloat16 *dst = reinterpret_cast<__nv_bfloat16 *>(ep.out) + (size_t)m * ep.ld_out + n;
-        if (full && (ep.ld_out % 8) == 0) {
-            uint4 *d4 = reinterpret_cast<uint4 *>(dst);
+    for (int ch = 0; ch < 8; ch++)
+        sts128(row + ((ch ^ (lane & 7)) << 4), r[4 * ch], r[4 * ch + 1], r[4 * ch + 2], r[4 * ch + 3]);
+}
+
+// per-lane column parameters of phase B (this lane's 4 columns nn .. nn+3), fetched BEFORE the TMEM load so
+// their latency hides under it
+struct ColParams { float bias[4]; float gate[4]; };
+
+template <int MODE>
+__device__ __forceinline__ void load_col_params(const GaGemmEpilogue &ep, int lane, int m0w, int n, int N, ColParams &cp)
+{
+    const int nn = n + (lane & 7) * 4;
 #pragma unroll
-            for (int i = 0; i < 4; i++)
-                d4[i] = make_uint4(pack_bf16(v[8 * i], v[8 * i + 1]), pack_bf16(v[8 * i + 2], v[8 * i + 3]),
-                                   pack_bf16(v[8 * i + 4], v[8 * i + 5]), pack_bf16(v[8 * i + 6], v[8 * i + 7]));
-        } else {
-#pragma unroll
-            for (int i = 0; i < 32; i++) if (n + i < N) dst[i] = __float2bfloat16(v[i]);
-        }
-        break;
+    for (int j = 0; j < 4; j++) {
+        cp.bias[j] = (ep.bias && nn + j < N) ? __ldg(ep.bias + nn + j) : 0.f;
+        cp.gate[j] = 1.f;
     }
-    case GA_EPI_F32: {
-        float *dst = reinterpret_cast<float *>(ep.out) + (size_t)m * ep.ld_out + n;
-        if (full && (ep.ld_out % 4) == 0) {
-            float4 *d4 = reinterpret_cast<float4 *>(dst);
+    if (MODE == GA_EPI_RESID_GATE_F32 && ep.gate) {
+        const int b = m0w / ep.rows_per_batch;           // used when the warp's 32 rows sit in one batch element
 #pragma unroll
-            for (int i = 0; i < 8; i++) d4[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-        } else {
-#pragma unroll
-            for (int i = 0; i < 32; i++) if (n + i < N) dst[i] = v[i];
-        }
-        break;
-    }
-    case GA_EPI_RESID_GATE_F32: {
-        // x[m, n] += gate[b, n] * (acc + bias)
-        float *dst = reinterpret_cast<float *>(ep.out) + (size_t)m * ep.ld_out + n;
-        const float *g = ep.gate ? ep.gate + (size_t)(m / ep.rows_per_batch) * ep.gate_ld + n : nullptr;
-        if (full && (ep.ld_out % 4) == 0 && (!g || (ep.gate_ld % 4) == 0)) {
-            float4 *d4 = reinterpret_cast<float4 *>(dst);
-            const float4 *g4 = reinterpret_cast<const float4 *>(g);
-#pragma unroll
-            for (int i = 0; i < 8; i++) {
-                float4 x = d4[i];
-                const float4 gg = g ? __ldg(g4 + i) : make_float4(1.f, 1.f, 1.f, 1.f);
-                x.x += gg.x * v[4 * i]; x.y += gg.y * v[4 * i + 1]; x.z += gg.z * v[4 * i + 2]; x.w += gg.w * v[4 * i + 3];
-                d4[i] = x;
-            }
-        } else {
-#pragma unroll
-            for (int i = 0; i < 32; i++) if (n + i < N) dst[i] += (g ? __ldg(g + i) : 1.f) * v[i];
-        }
-        break;
-    }
-    default: break;
+        for (int j = 0; j < 4; j++) if (nn + j < N) cp.gate[j] = __ldg(ep.gate + (size_t)b * ep.gate_ld + nn + j);
     }
 }
 
-// HEADS epilogue for one head (64 columns [n, n+64)): two TMEM passes keep the live set at 32 values.
-//   which = n / inner (+ first_part): 0 q, 1 k, 2 v ; head = (n % inner) / 64   ("(K H D)" column layout,
-//   vit/vision_transformer.py:191,255).  q/k: per-head RMSNorm (dit/norm.py:27-40), fp32, then * weight.
-__device__ __forceinline__ void epilogue_head(const GaGemmEpilogue &ep, uint32_t taddr, int m, int n, int M)
+// 32 fp32 accumulator columns [n, n+32) of the warp's 32 rows [m0w, m0w+32), already staged by stage_rows()
+template <int MODE>
+__device__ __forceinline__ void epilogue32(const GaGemmEpilogue &ep, uint32_t stg, int lane, int m0w, int n, int M, int N,
+                                           const ColParams &cp)
+{
+    const int ch = lane & 7, rsub = lane >> 3;
+    const int nn = n + ch * 4;                                 // this lane's 4 columns
+    const bool vec = (nn + 4 <= N) && (ep.ld_out % 4) == 0;
+    bool one_batch = true;
+    if (MODE == GA_EPI_RESID_GATE_F32 && ep.gate)
+        one_batch = (m0w + 31) / ep.rows_per_batch == m0w / ep.rows_per_batch;
+    uint4 acc[8];
+#pragma unroll
+    for (int it = 0; it < 8; it++) {
+        const int rr = it * 4 + rsub;
+        acc[it] = lds128(stg + rr * 128 + ((ch ^ (rr & 7)) << 4));
+    }
+    if (nn >= N) return;
+#pragma unroll
+    for (int it = 0; it < 8; it++) {
+        const int m = m0w + it * 4 + rsub;
+        if (m >= M) continue;
+        float v[4] = {__uint_as_float(acc[it].x) + cp.bias[0], __uint_as_float(acc[it].y) + cp.bias[1],
+                      __uint_as_float(acc[it].z) + cp.bias[2], __uint_as_float(acc[it].w) + cp.bias[3]};
+        if (MODE == GA_EPI_BF16 || MODE == GA_EPI_GELU_BF16) {
+            if (MODE == GA_EPI_GELU_BF16) {
+#pragma unroll
+                for (int j = 0; j < 4; j++) v[j] = gelu_erf(v[j]);
+            }
+            __nv_bfloat16 *dst = reinterpret_cast<__nv_bfloat16 *>(ep.out) + (size_t)m * ep.ld_out + nn;
+            if (vec) {
+                *reinterpret_cast<uint2 *>(dst) = make_uint2(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]));
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; j++) if (nn + j < N) dst[j] = __float2bfloat16(v[j]);
+            }
+        } else if (MODE == GA_EPI_F32) {
+            float *dst = reinterpret_cast<float *>(ep.out) + (size_t)m * ep.ld_out + nn;
+            if (vec) {
+                *reinterpret_cast<float4 *>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; j++) if (nn + j < N) dst[j] = v[j];
+            }
+        } else if (MODE == GA_EPI_RESID_GATE_F32) {
+            // x[m, n] += gate[b, n] * (acc + bias)
+            float *dst = reinterpret_cast<float *>(ep.out) + (size_t)m * ep.ld_out + nn;
+            float g[4] = {cp.gate[0], cp.gate[1], cp.gate[2], cp.gate[3]};
+            if (!one_batch) {
+                const float *gp = ep.gate + (size_t)(m / ep.rows_per_batch) * ep.gate_ld + nn;
+#pragma unroll
+                for (int j = 0; j < 4; j++) if (nn + j < N) g[j] = __ldg(gp + j);
+            }
+            if (vec) {
+                float4 x = *reinterpret_cast<float4 *>(dst);
+                x.x += g[0] * v[0]; x.y += g[1] * v[1]; x.z += g[2] * v[2]; x.w += g[3] * v[3];
+                *reinterpret_cast<float4 *>(dst) = x;
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; j++) if (nn + j < N) dst[j] += g[j] * v[j];
+            }
+        }
+    }
+}
+
+// HEADS epilogue for one head (64 columns [n, n+64)) of the warp's 32 rows: two TMEM passes keep the live set at
+// 32 values.  which = n / inner (+ first_part): 0 q, 1 k, 2 v ; head = (n % inner) / 64   ("(K H D)" column
+// layout, vit/vision_transformer.py:191,255).  q/k: per-head RMSNorm (dit/norm.py:27-40), fp32, then * weight;
+// a token's 64 bf16 are one 128 B line of the [B, H, tok_pitch, 64] layout.  v is stored transposed per head,
+// [B, H, 64, tok_pitch], so that P*V is a K-major x K-major contraction: staged as [d][32 tokens].
+__device__ __forceinline__ void epilogue_head(const GaGemmEpilogue &ep, uint32_t stg, float *hp, uint32_t taddr, int lane,
+                                              int m0w, int n, int M)
 {
     const int inner = ep.heads * 64;
     const int which = n / inner + ep.first_part;
     const int head = (n % inner) / 64;
-    const int mm = m < M ? m : 0;
-    const int b = mm / ep.rows_per_batch, t = mm % ep.rows_per_batch;
-    const size_t bh = (size_t)b * ep.heads + head;
+    const float *w = which == 0 ? ep.qn_w : (which == 1 ? ep.kn_w : nullptr);
+    hp[lane] = ep.bias ? __ldg(ep.bias + n + lane) : 0.f;
+    hp[32 + lane] = ep.bias ? __ldg(ep.bias + n + 32 + lane) : 0.f;
+    hp[64 + lane] = w ? __ldg(w + lane) : 1.f;
+    hp[96 + lane] = w ? __ldg(w + 32 + lane) : 1.f;
+    __syncwarp();
+    const int rpb = ep.rows_per_batch;
+    const int b_first = m0w / rpb;
+    const bool one_batch = (m0w + 31) / rpb == b_first;
     uint32_t r[32];
     float rs = 1.0f;
-    const float *w = which == 0 ? ep.qn_w : (which == 1 ? ep.kn_w : nullptr);
     if (w) {
         float ss = 0.f;
 #pragma unroll
@@ -137,35 +205,123 @@ __device__ __forceinline__ void epilogue_head(const GaGemmEpilogue &ep, uint32_t
             tmem_ld_wait();
 #pragma unroll
             for (int i = 0; i < 32; i++) {
-                const float x = __uint_as_float(r[i]) + (ep.bias ? __ldg(ep.bias + n + h2 * 32 + i) : 0.f);
+                const float x = __uint_as_float(r[i]) + hp[h2 * 32 + i];
                 ss += x * x;
             }
         }
         rs = rsqrtf(ss * (1.0f / 64.0f) + ep.eps);
     }
+    if (which <= 1) {
 #pragma unroll
-    for (int h2 = 0; h2 < 2; h2++) {
-        tmem_ld_32x32b_x32(taddr + h2 * 32, r);
-        tmem_ld_wait();
-        float v[32];
+        for (int h2 = 0; h2 < 2; h2++) {
+            tmem_ld_32x32b_x32(taddr + h2 * 32, r);
+            tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; i++) {
-            v[i] = __uint_as_float(r[i]) + (ep.bias ? __ldg(ep.bias + n + h2 * 32 + i) : 0.f);
-            if (w) v[i] = v[i] * rs * __ldg(w + h2 * 32 + i);
+            for (int c4 = 0; c4 < 4; c4++) {
+                uint32_t pk[4];
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const int i = c4 * 8 + j * 2;
+                    const float x0 = (__uint_as_float(r[i]) + hp[h2 * 32 + i]) * rs * hp[64 + h2 * 32 + i];
+                    const float x1 = (__uint_as_float(r[i + 1]) + hp[h2 * 32 + i + 1]) * rs * hp[64 + h2 * 32 + i + 1];
+                    pk[j] = pack_bf16(x0, x1);
+                }
+                sts128(stg + lane * 128 + (((h2 * 4 + c4) ^ (lane & 7)) << 4), pk[0], pk[1], pk[2], pk[3]);
+            }
         }
-        if (m >= M) continue;
-        if (which <= 1) {
-            __nv_bfloat16 *base = reinterpret_cast<__nv_bfloat16 *>(which == 0 ? ep.q : ep.k);
-            uint4 *d4 = reinterpret_cast<uint4 *>(base + (bh * ep.tok_pitch + t) * 64 + h2 * 32);
+        warp_sync_smem();
+        __nv_bfloat16 *base = reinterpret_cast<__nv_bfloat16 *>(which == 0 ? ep.q : ep.k);
+        const int ch = lane & 7, rsub = lane >> 3;
+        uint4 x[8];
 #pragma unroll
-            for (int i = 0; i < 4; i++)
-                d4[i] = make_uint4(pack_bf16(v[8 * i], v[8 * i + 1]), pack_bf16(v[8 * i + 2], v[8 * i + 3]),
-                                   pack_bf16(v[8 * i + 4], v[8 * i + 5]), pack_bf16(v[8 * i + 6], v[8 * i + 7]));
-        } else {
-            // V stored transposed per head, [B, H, 64, tok_pitch]: P*V becomes a K-major x K-major contraction
-            __nv_bfloat16 *base = reinterpret_cast<__nv_bfloat16 *>(ep.vt) + (bh * 64 + h2 * 32) * ep.tok_pitch + t;
+        for (int it = 0; it < 8; it++) {
+            const int rr = it * 4 + rsub;
+            x[it] = lds128(stg + rr * 128 + ((ch ^ (rr & 7)) << 4));
+        }
 #pragma unroll
-            for (int i = 0; i < 32; i++) base[(size_t)i * ep.tok_pitch] = __float2bfloat16(v[i]);
+        for (int it = 0; it < 8; it++) {
+            const int m = m0w + it * 4 + rsub;
+            if (m >= M) continue;
+            const int b = one_batch ? b_first : m / rpb;
+            const int t = m - b * rpb;
+            *reinterpret_cast<uint4 *>(base + (((size_t)b * ep.heads + head) * ep.tok_pitch + t) * 64 + ch * 8) = x[it];
+        }
+    } else {
+        const int t0 = m0w - b_first * rpb;
+        const bool fast = one_batch && (m0w + 32 <= M) && (ep.tok_pitch % 8) == 0 && (t0 % 8) == 0;
+        __nv_bfloat16 *vt = reinterpret_cast<__nv_bfloat16 *>(ep.vt);
+#pragma unroll
+        for (int h2 = 0; h2 < 2; h2++) {
+            tmem_ld_32x32b_x32(taddr + h2 * 32, r);
+            tmem_ld_wait();
+            if (fast) {
+#pragma unroll
+                for (int i = 0; i < 32; i++) {
+                    const __nv_bfloat16 hv = __float2bfloat16(__uint_as_float(r[i]) + hp[h2 * 32 + i]);
+                    asm volatile("st.shared.b16 [%0], %1;\n" ::"r"(stg + (uint32_t)((h2 * 32 + i) * 64 + lane * 2)),
+                                 "h"(*reinterpret_cast<const unsigned short *>(&hv)));
+                }
+            } else {
+                const int m = m0w + lane;
+                if (m < M) {
+                    const int b = m / rpb, t = m - b * rpb;
+                    __nv_bfloat16 *dst = vt + (((size_t)b * ep.heads + head) * 64 + h2 * 32) * ep.tok_pitch + t;
+#pragma unroll
+                    for (int i = 0; i < 32; i++)
+                        dst[(size_t)i * ep.tok_pitch] = __float2bfloat16(__uint_as_float(r[i]) + hp[h2 * 32 + i]);
+                }
+            }
+        }
+        if (fast) {
+            warp_sync_smem();
+            const int ch = lane & 3, dsub = lane >> 2;
+            uint4 x[8];
+#pragma unroll
+            for (int it = 0; it < 8; it++) x[it] = lds128(stg + (it * 8 + dsub) * 64 + ch * 16);
+#pragma unroll
+            for (int it = 0; it < 8; it++) {
+                const int dd = it * 8 + dsub;
+                *reinterpret_cast<uint4 *>(vt + (((size_t)b_first * ep.heads + head) * 64 + dd) * ep.tok_pitch + t0 + ch * 8) =
+                    x[it];
+            }
+        }
+    }
+    warp_sync_smem();       // staging buffer and hp[] are rewritten by the next call
+}
+
+// One epilogue warp drains its half of the BN accumulator columns for its 32 rows.
+template <int BN, int MODE>
+__device__ __forceinline__ void epilogue_tile(const GaGemmEpilogue &ep, uint32_t stg, float *hp, uint32_t trow, int lane,
+                                              int chalf, int m0w, int n0, int M, int N)
+{
+    if (MODE == GA_EPI_HEADS) {
+#pragma unroll 1
+        for (int c = chalf * (BN / 2); c < (chalf + 1) * (BN / 2); c += 64)
+            if (n0 + c < N) epilogue_head(ep, stg, hp, trow + c, lane, m0w, n0 + c, M);
+    } else {
+        const int c0 = chalf * (BN / 2), c1 = (chalf + 1) * (BN / 2);
+        if (n0 + c0 >= N) return;                                  // warp-uniform
+        // software pipeline over the 32-column chunks: the TMEM load of chunk c+1 is in flight while chunk c is
+        // staged and stored
+        uint32_t r[32];
+        ColParams cp;
+        load_col_params<MODE>(ep, lane, m0w, n0 + c0, N, cp);
+        tmem_ld_32x32b_x32(trow + c0, r);
+#pragma unroll 1
+        for (int c = c0; c < c1; c += 32) {
+            if (n0 + c >= N) break;                                // warp-uniform
+            tmem_ld_wait();
+            stage_rows(stg, lane, r);
+            const bool more = (c + 32 < c1) && (n0 + c + 32 < N);
+            ColParams cpn;
+            if (more) {
+                tmem_ld_32x32b_x32(trow + c + 32, r);
+                load_col_params<MODE>(ep, lane, m0w, n0 + c + 32, N, cpn);
+            }
+            warp_sync_smem();
+            epilogue32<MODE>(ep, stg, lane, m0w, n0 + c, M, N, cp);
+            warp_sync_smem();
+            if (more) cp = cpn;
         }
     }
 }
@@ -175,7 +331,7 @@ __device__ __forceinline__ void epilogue_head(const GaGemmEpilogue &ep, uint32_t
 // CS > 1: a cluster of CS CTAs works on CS vertically adjacent tiles (same n-block).  Each CTA loads its own A
 // tile and 1/CS of the shared W tile, multicast to every CTA of the cluster, so the L2 -> SM operand traffic per
 // CTA drops from (128 + BN) to (128 + BN/CS) rows per k-block -- the main loop is L2-bandwidth bound otherwise.
-template <int BN, int CS>
+template <int BN, int CS, int MODE>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                     const GaGemmEpilogue ep, const int M, const int N, const int K)
@@ -266,7 +422,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
         const int ew = warp - 2;
         const int q = warp & 3;                     // TMEM lane quarter this warp may access
         const int chalf = ew >> 2;                  // which half of the BN columns this warp drains
-        const int row = q * 32 + lane;
+        const uint32_t stg = smem_u32(smem + Cfg::kRing + ew * kStageBytes);
+        float *hp = reinterpret_cast<float *>(smem + Cfg::kRing + kEpiWarps * kStageBytes) + ew * kHeadParams;
         int lt = 0;
         for (int tile = cid; tile < tiles; tile += ncl, lt++) {
             const int m0 = ((tile % num_mg) * CS + crank) * BM, n0 = (tile / num_mg) * BN;
@@ -274,27 +431,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
             mbar_wait(&acc_full[a], (lt >> 1) & 1);
             tc_fence_after();
             const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * BN);
-            const int m = m0 + row;
-            if (ep.mode == GA_EPI_HEADS) {
-#pragma unroll 1
-                for (int c = chalf * (BN / 2); c < (chalf + 1) * (BN / 2); c += 64)
-                    if (n0 + c < N) epilogue_head(ep, trow + c, m, n0 + c, M);
-            } else {
-#pragma unroll 1
-                for (int c = chalf * (BN / 2); c < (chalf + 1) * (BN / 2); c += 32) {
-                    if (n0 + c >= N) break;                       // warp-uniform
-                    uint32_t r[32];
-                    tmem_ld_32x32b_x32(trow + c, r);
-                    tmem_ld_wait();
-                    if (m < M) {
-                        float v[32];
-#pragma unroll
-                        for (int i = 0; i < 32; i++)
-                            v[i] = __uint_as_float(r[i]) + ((ep.bias && n0 + c + i < N) ? __ldg(ep.bias + n0 + c + i) : 0.f);
-                        epilogue32(ep, m, n0 + c, N, v);
-                    }
-                }
-            }
+            epilogue_tile<BN, MODE>(ep, stg, hp, trow, lane, chalf, m0 + q * 32, n0, M, N);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&acc_empty[a]);
@@ -317,12 +454,13 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
 template <int BN> struct PairCfg {
     static constexpr int kABytes = BM * BK * 2;                 // 16 KB
     static constexpr int kBBytes = (BN / 2) * BK * 2;           // this CTA's half of the W tile
-    static constexpr int kStages = (BN >= 256) ? 6 : 8;
-    static constexpr int kSmem = kStages * (kABytes + kBBytes) + 1024;
+    static constexpr int kStages = (BN >= 256) ? 5 : 7;
+    static constexpr int kRing = kStages * (kABytes + kBBytes);
+    static constexpr int kSmem = kRing + 1024 + 36 * 1024;
     static constexpr int kTmemCols = 2 * BN;
 };
 
-template <int BN>
+template <int BN, int MODE>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_bf16_tn_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                          const GaGemmEpilogue ep, const int M, const int N, const int K)
@@ -404,7 +542,8 @@ gemm_bf16_tn_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
         const int ew = warp - 2;
         const int q = warp & 3;
         const int chalf = ew >> 2;
-        const int row = q * 32 + lane;
+        const uint32_t stg = smem_u32(smem + Cfg::kRing + ew * kStageBytes);
+        float *hp = reinterpret_cast<float *>(smem + Cfg::kRing + kEpiWarps * kStageBytes) + ew * kHeadParams;
         int lt = 0;
         for (int tile = cid; tile < tiles; tile += ncl, lt++) {
             const int m0 = ((tile % num_mg) * 2 + crank) * BM, n0 = (tile / num_mg) * BN;
@@ -412,27 +551,7 @@ gemm_bf16_tn_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
             mbar_wait(&acc_full[a], (lt >> 1) & 1);
             tc_fence_after();
             const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * BN);
-            const int m = m0 + row;
-            if (ep.mode == GA_EPI_HEADS) {
-#pragma unroll 1
-                for (int c = chalf * (BN / 2); c < (chalf + 1) * (BN / 2); c += 64)
-                    if (n0 + c < N) epilogue_head(ep, trow + c, m, n0 + c, M);
-            } else {
-#pragma unroll 1
-                for (int c = chalf * (BN / 2); c < (chalf + 1) * (BN / 2); c += 32) {
-                    if (n0 + c >= N) break;
-                    uint32_t r[32];
-                    tmem_ld_32x32b_x32(trow + c, r);
-                    tmem_ld_wait();
-                    if (m < M) {
-                        float v[32];
-#pragma unroll
-                        for (int i = 0; i < 32; i++)
-                            v[i] = __uint_as_float(r[i]) + ((ep.bias && n0 + c + i < N) ? __ldg(ep.bias + n0 + c + i) : 0.f);
-                        epilogue32(ep, m, n0 + c, N, v);
-                    }
-                }
-            }
+            epilogue_tile<BN, MODE>(ep, stg, hp, trow, lane, chalf, m0 + q * 32, n0, M, N);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {
@@ -498,19 +617,14 @@ static int sm_count()
     return num_sms;
 }
 
-template <int BN, int CS>
-static int launch_gemm(const void *A, int lda, const void *W, int ldw, const GaGemmEpilogue &ep, int M, int N, int K,
-                       cudaStream_t s)
+template <int BN, int CS, int MODE>
+static int launch_gemm_mode(const CUtensorMap &ta, const CUtensorMap &tb, const GaGemmEpilogue &ep, int M, int N, int K,
+                            cudaStream_t s)
 {
     using Cfg = GemmCfg<BN>;
-    CUtensorMap ta, tb;
-    int rc = ga_make_tmap_bf16(&ta, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, BM);
-    if (rc) return rc;
-    rc = ga_make_tmap_bf16(&tb, W, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, (uint32_t)(BN / CS));
-    if (rc) return rc;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tn_kernel<BN, CS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tn_kernel<BN, CS, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              Cfg::kSmem);
         if (e != cudaSuccess) return (int)e;
         attr_set = true;
@@ -521,24 +635,41 @@ static int launch_gemm(const void *A, int lda, const void *W, int ldw, const GaG
     if (items < clusters) clusters = items;
     dim3 grid(clusters * CS);
     if (CS == 1)
-        return (int)ga_launch_pdl(gemm_bf16_tn_kernel<BN, CS>, grid, dim3(kThreads), (size_t)Cfg::kSmem, s, ta, tb, ep, M, N, K);
-    return (int)ga_launch_cluster(gemm_bf16_tn_kernel<BN, CS>, grid, dim3(kThreads), (size_t)Cfg::kSmem, s, (unsigned)CS, ta,
-                                  tb, ep, M, N, K);
+        return (int)ga_launch_pdl(gemm_bf16_tn_kernel<BN, CS, MODE>, grid, dim3(kThreads), (size_t)Cfg::kSmem, s, ta, tb, ep,
+                                  M, N, K);
+    return (int)ga_launch_cluster(gemm_bf16_tn_kernel<BN, CS, MODE>, grid, dim3(kThreads), (size_t)Cfg::kSmem, s,
+                                  (unsigned)CS, ta, tb, ep, M, N, K);
 }
 
-template <int BN>
-static int launch_gemm_pair(const void *A, int lda, const void *W, int ldw, const GaGemmEpilogue &ep, int M, int N, int K,
-                            cudaStream_t s)
+template <int BN, int CS>
+static int launch_gemm(const void *A, int lda, const void *W, int ldw, const GaGemmEpilogue &ep, int M, int N, int K,
+                       cudaStream_t s)
 {
-    using Cfg = PairCfg<BN>;
     CUtensorMap ta, tb;
     int rc = ga_make_tmap_bf16(&ta, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, BM);
     if (rc) return rc;
-    rc = ga_make_tmap_bf16(&tb, W, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, (uint32_t)(BN / 2));
+    rc = ga_make_tmap_bf16(&tb, W, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, (uint32_t)(BN / CS));
     if (rc) return rc;
+    switch (ep.mode) {
+    case GA_EPI_BF16: return launch_gemm_mode<BN, CS, GA_EPI_BF16>(ta, tb, ep, M, N, K, s);
+    case GA_EPI_GELU_BF16: return launch_gemm_mode<BN, CS, GA_EPI_GELU_BF16>(ta, tb, ep, M, N, K, s);
+    case GA_EPI_F32: return launch_gemm_mode<BN, CS, GA_EPI_F32>(ta, tb, ep, M, N, K, s);
+    case GA_EPI_RESID_GATE_F32: return launch_gemm_mode<BN, CS, GA_EPI_RESID_GATE_F32>(ta, tb, ep, M, N, K, s);
+    case GA_EPI_HEADS:
+        if (BN >= 128) return launch_gemm_mode<(BN >= 128 ? BN : 128), CS, GA_EPI_HEADS>(ta, tb, ep, M, N, K, s);
+        return GA_ERR_BADARG;
+    default: return GA_ERR_BADARG;
+    }
+}
+
+template <int BN, int MODE>
+static int launch_gemm_pair_mode(const CUtensorMap &ta, const CUtensorMap &tb, const GaGemmEpilogue &ep, int M, int N, int K,
+                                 cudaStream_t s)
+{
+    using Cfg = PairCfg<BN>;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tn_pair_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tn_pair_kernel<BN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              Cfg::kSmem);
         if (e != cudaSuccess) return (int)e;
         attr_set = true;
@@ -547,15 +678,34 @@ static int launch_gemm_pair(const void *A, int lda, const void *W, int ldw, cons
     const int items = ((num_m + 1) / 2) * num_n;
     int pairs = sm_count() / 2;
     if (items < pairs) pairs = items;
-    return (int)ga_launch_cluster(gemm_bf16_tn_pair_kernel<BN>, dim3(pairs * 2), dim3(kThreads), (size_t)Cfg::kSmem, s, 2u, ta,
-                                  tb, ep, M, N, K);
+    return (int)ga_launch_cluster(gemm_bf16_tn_pair_kernel<BN, MODE>, dim3(pairs * 2), dim3(kThreads), (size_t)Cfg::kSmem, s,
+                                  2u, ta, tb, ep, M, N, K);
+}
+
+template <int BN>
+static int launch_gemm_pair(const void *A, int lda, const void *W, int ldw, const GaGemmEpilogue &ep, int M, int N, int K,
+                            cudaStream_t s)
+{
+    CUtensorMap ta, tb;
+    int rc = ga_make_tmap_bf16(&ta, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, BM);
+    if (rc) return rc;
+    rc = ga_make_tmap_bf16(&tb, W, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, (uint32_t)(BN / 2));
+    if (rc) return rc;
+    switch (ep.mode) {
+    case GA_EPI_BF16: return launch_gemm_pair_mode<BN, GA_EPI_BF16>(ta, tb, ep, M, N, K, s);
+    case GA_EPI_GELU_BF16: return launch_gemm_pair_mode<BN, GA_EPI_GELU_BF16>(ta, tb, ep, M, N, K, s);
+    case GA_EPI_F32: return launch_gemm_pair_mode<BN, GA_EPI_F32>(ta, tb, ep, M, N, K, s);
+    case GA_EPI_RESID_GATE_F32: return launch_gemm_pair_mode<BN, GA_EPI_RESID_GATE_F32>(ta, tb, ep, M, N, K, s);
+    case GA_EPI_HEADS: return launch_gemm_pair_mode<BN, GA_EPI_HEADS>(ta, tb, ep, M, N, K, s);
+    default: return GA_ERR_BADARG;
+    }
 }
 
 extern "C" int ga_gemm_bf16_tn(const void *A, int lda, const void *W, int ldw, int M, int N, int K,
                                const GaGemmEpilogue *epi, int block_n, void *stream)
 {
     if (!A || !W || !epi || M <= 0 || N <= 0 || K <= 0) return GA_ERR_BADARG;
-    // block_n = tile width {64,128,256} + 1000 * cluster size {1 (default), 2, 4}; 9000 + width = CTA pair
+    // block_n = tile width {64,128,256} + 1000 * cluster size {1 (default), 2}; 9000 + width = CTA pair
     const int cs = block_n >= 1000 ? block_n / 1000 : 1;
     const int bn = block_n % 1000;
     if (epi->mode == GA_EPI_HEADS && (N % 64 != 0 || epi->heads <= 0 || bn < 128)) return GA_ERR_BADARG;
@@ -569,10 +719,6 @@ extern "C" int ga_gemm_bf16_tn(const void *A, int lda, const void *W, int ldw, i
     if (cs == 2) {
         if (bn == 128) return launch_gemm<128, 2>(A, lda, W, ldw, *epi, M, N, K, s);
         if (bn == 256) return launch_gemm<256, 2>(A, lda, W, ldw, *epi, M, N, K, s);
-    }
-    if (cs == 4) {
-        if (bn == 128) return launch_gemm<128, 4>(A, lda, W, ldw, *epi, M, N, K, s);
-        if (bn == 256) return launch_gemm<256, 4>(A, lda, W, ldw, *epi, M, N, K, s);
     }
     if (cs == 9) {          // 9xxx: CTA pair (cta_group::2), 256 x bn tile per pair
         if (bn == 128) return launch_gemm_pair<128>(A, lda, W, ldw, *epi, M, N, K, s);

@@ -118,39 +118,49 @@ __device__ __forceinline__ void block_bitonic_sort(unsigned long long *a, int n)
 
 // Warp-level bitonic sort of up to 32*KPL keys held in registers, element i = r*32 + lane (striped, so global
 // loads/stores are coalesced): partner distances < 32 are shuffles, distances >= 32 stay inside the lane.
-// No shared memory and no block barrier -- a typical tile (~170 instances) costs ~1.6k warp instructions.
+// No shared memory and no block barrier.  Only the in-lane stages (static register indices) are unrolled; the
+// shuffle stages run as a loop over the distance -- fully unrolled, the four instantiations came to 27k
+// instructions and the kernel spent half its time on instruction-cache misses (profiles/r01_raster_small.md).
+template <int KPL>
+__device__ __forceinline__ void warp_shuffle_stages(unsigned long long (&v)[KPL], int lane, int k, int jstart)
+{
+#pragma unroll 1
+    for (int j = jstart; j >= 1; j >>= 1) {
+        const bool lower = (lane & j) == 0;
+#pragma unroll
+        for (int r = 0; r < KPL; r++) {
+            const bool asc = ((((r << 5) | lane) & k) == 0);
+            const unsigned long long mine = v[r];
+            const unsigned long long other = __shfl_xor_sync(0xffffffffu, mine, j);
+            const bool keep_min = (lower == asc);
+            v[r] = keep_min ? (mine < other ? mine : other) : (mine > other ? mine : other);
+        }
+    }
+}
+
 template <int KPL>
 __device__ __forceinline__ void warp_bitonic_sort(unsigned long long (&v)[KPL], int lane)
 {
     constexpr int N = 32 * KPL;
+#pragma unroll 1
+    for (int k = 2; k <= 32; k <<= 1) warp_shuffle_stages<KPL>(v, lane, k, k >> 1);
 #pragma unroll
-    for (int k = 2; k <= N; k <<= 1) {
+    for (int k = 64; k <= N; k <<= 1) {
 #pragma unroll
-        for (int j = k >> 1; j >= 1; j >>= 1) {
-            if (j >= 32) {
-                const int jr = j >> 5;
+        for (int j = k >> 1; j >= 32; j >>= 1) {
+            const int jr = j >> 5;
 #pragma unroll
-                for (int r = 0; r < KPL; r++) {
-                    if ((r & jr) == 0) {
-                        const bool asc = (((r << 5) & k) == 0);              // k >= 64 here: decided by r alone
-                        unsigned long long a = v[r], b = v[r | jr];
-                        const bool sw = asc ? (a > b) : (a < b);
-                        v[r] = sw ? b : a;
-                        v[r | jr] = sw ? a : b;
-                    }
-                }
-            } else {
-                const bool lower = (lane & j) == 0;
-#pragma unroll
-                for (int r = 0; r < KPL; r++) {
-                    const bool asc = ((((r << 5) | lane) & k) == 0);
-                    const unsigned long long mine = v[r];
-                    const unsigned long long other = __shfl_xor_sync(0xffffffffu, mine, j);
-                    const bool keep_min = (lower == asc);
-                    v[r] = keep_min ? (mine < other ? mine : other) : (mine > other ? mine : other);
+            for (int r = 0; r < KPL; r++) {
+                if ((r & jr) == 0) {
+                    const bool asc = (((r << 5) & k) == 0);              // k >= 64 here: decided by r alone
+                    unsigned long long a = v[r], b = v[r | jr];
+                    const bool sw = asc ? (a > b) : (a < b);
+                    v[r] = sw ? b : a;
+                    v[r | jr] = sw ? a : b;
                 }
             }
         }
+        warp_shuffle_stages<KPL>(v, lane, k, 16);
     }
 }
 
@@ -232,7 +242,7 @@ cudaError_t ga_launch_binning(const RasterDims &d, const RasterWs &w, cudaStream
     dim3 grid((d.P + 255) / 256, d.NV);
     scatter_kernel<<<grid, 256, 0, s>>>(d, w);
     sort_tiles_warp_kernel<<<(d.NV * d.T + 7) / 8, 256, 0, s>>>(d, w);
-    const int big_grid = d.NV * d.T < 592 ? d.NV * d.T : 592;
+    const int big_grid = d.NV * d.T < 148 * 7 ? d.NV * d.T : 148 * 7;      // 32 KB of keys per block: 7 blocks per SM
     sort_tiles_kernel<<<big_grid, 256, 0, s>>>(d, w);
     return cudaGetLastError();
 }

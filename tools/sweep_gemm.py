@@ -13,17 +13,20 @@ dev = torch.device("cuda:0")
 st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
 shapes = [(4096, 768, 768), (4096, 2304, 768), (4096, 3072, 768), (4096, 768, 3072),
           (1536, 1024, 1024), (1536, 3072, 1024), (1536, 4096, 1024), (1536, 1024, 4096), (2738, 1536, 1024)]
-cfgs = [128, 256, 9128, 9256]
+cfgs = [128, 256, 2128, 9128, 9256]
+MODE = dit.EPI_GELU_BF16 if "gelu" in sys.argv else dit.EPI_BF16
 for (M, N, K) in shapes:
     torch.manual_seed(0)
     A = torch.randn(M, K, device=dev).bfloat16()
     W = (torch.randn(N, K, device=dev) / math.sqrt(K)).bfloat16()
     bias = torch.randn(N, device=dev)
     ref = A.float() @ W.float().T + bias
+    if MODE == dit.EPI_GELU_BF16:
+        ref = torch.nn.functional.gelu(ref)
     row = []
     for cfg in cfgs:
         out = torch.zeros(M, N, device=dev, dtype=torch.bfloat16)
-        e = dit.GaGemmEpilogue(mode=dit.EPI_BF16, bias=bias.data_ptr(), out=out.data_ptr(), ld_out=N)
+        e = dit.GaGemmEpilogue(mode=MODE, bias=bias.data_ptr(), out=out.data_ptr(), ld_out=N)
         rc = L.ga_gemm_bf16_tn(dit._p(A), K, dit._p(W), K, M, N, K, C.byref(e), cfg, st)
         torch.cuda.synchronize()
         if rc != 0:
