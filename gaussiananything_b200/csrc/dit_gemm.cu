@@ -127,6 +127,18 @@ __device__ __forceinline__ void epilogue32(const GaGemmEpilogue &ep, uint32_t st
         const int rr = it * 4 + rsub;
         acc[it] = lds128(stg + rr * 128 + ((ch ^ (rr & 7)) << 4));
     }
+    // residual rows are read up front, all eight in flight at once: interleaved with the stores below the compiler
+    // must assume they alias and the loop degenerates into eight serial L2 round trips per chunk
+    float4 res[8];
+    if (MODE == GA_EPI_RESID_GATE_F32 && vec) {
+#pragma unroll
+        for (int it = 0; it < 8; it++) {
+            const int m = m0w + it * 4 + rsub;
+            res[it] = (m < M) ? *reinterpret_cast<const float4 *>(reinterpret_cast<const float *>(ep.out) +
+                                                                   (size_t)m * ep.ld_out + nn)
+                              : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
     if (nn >= N) return;
 #pragma unroll
     for (int it = 0; it < 8; it++) {
@@ -164,7 +176,7 @@ __device__ __forceinline__ void epilogue32(const GaGemmEpilogue &ep, uint32_t st
                 for (int j = 0; j < 4; j++) if (nn + j < N) g[j] = __ldg(gp + j);
             }
             if (vec) {
-                float4 x = *reinterpret_cast<float4 *>(dst);
+                float4 x = res[it];
                 x.x += g[0] * v[0]; x.y += g[1] * v[1]; x.z += g[2] * v[2]; x.w += g[3] * v[3];
                 *reinterpret_cast<float4 *>(dst) = x;
             } else {

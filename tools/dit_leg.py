@@ -1,0 +1,12 @@
+"""Time only the DiT legs of bench.py (C3 sampler + deployed DiT-L): python tools/dit_leg.py"""
+import json
+import sys
+
+import torch
+
+sys.path.insert(0, ".")
+import bench  # noqa: E402
+
+dev = torch.device("cuda:0")
+print(json.dumps(bench.run_dit_leg(dev)))
+print(json.dumps(bench.run_dit_deployed_leg(dev)))

@@ -14,7 +14,7 @@ st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
 shapes = [(4096, 768, 768), (4096, 2304, 768), (4096, 3072, 768), (4096, 768, 3072),
           (1536, 1024, 1024), (1536, 3072, 1024), (1536, 4096, 1024), (1536, 1024, 4096), (2738, 1536, 1024)]
 cfgs = [128, 256, 2128, 9128, 9256]
-MODE = dit.EPI_GELU_BF16 if "gelu" in sys.argv else dit.EPI_BF16
+MODE = dit.EPI_GELU_BF16 if "gelu" in sys.argv else (dit.EPI_RESID_GATE_F32 if "resid" in sys.argv else dit.EPI_BF16)
 for (M, N, K) in shapes:
     torch.manual_seed(0)
     A = torch.randn(M, K, device=dev).bfloat16()
@@ -25,15 +25,21 @@ for (M, N, K) in shapes:
         ref = torch.nn.functional.gelu(ref)
     row = []
     for cfg in cfgs:
-        out = torch.zeros(M, N, device=dev, dtype=torch.bfloat16)
-        e = dit.GaGemmEpilogue(mode=MODE, bias=bias.data_ptr(), out=out.data_ptr(), ld_out=N)
+        if MODE == dit.EPI_RESID_GATE_F32:
+            out = torch.zeros(M, N, device=dev, dtype=torch.float32)
+            gate = torch.ones(2, N, device=dev)
+            e = dit.GaGemmEpilogue(mode=MODE, bias=bias.data_ptr(), out=out.data_ptr(), ld_out=N, gate=gate.data_ptr(),
+                                   gate_ld=N, rows_per_batch=M // 2)
+        else:
+            out = torch.zeros(M, N, device=dev, dtype=torch.bfloat16)
+            e = dit.GaGemmEpilogue(mode=MODE, bias=bias.data_ptr(), out=out.data_ptr(), ld_out=N)
         rc = L.ga_gemm_bf16_tn(dit._p(A), K, dit._p(W), K, M, N, K, C.byref(e), cfg, st)
         torch.cuda.synchronize()
         if rc != 0:
             row.append("%5d: rc=%d" % (cfg, rc))
             continue
         err = float((out.float() - ref).norm() / ref.norm())
-        for _ in range(3):
+        for _ in range(3 if MODE != dit.EPI_RESID_GATE_F32 else 0):
             L.ga_gemm_bf16_tn(dit._p(A), K, dit._p(W), K, M, N, K, C.byref(e), cfg, st)
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
