@@ -65,7 +65,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
                 const float scale_log2, const float bound_log2)
 {
     extern __shared__ uint8_t smem_raw[];
-    __shared__ uint64_t q_full, k_full[2], k_empty[2], v_full, v_empty, s_full, p_full, o_full, o_empty, p_empty;
+    __shared__ uint64_t q_full, k_full[2], k_empty[2], v_full, v_empty, s_full, s_empty, p_full, o_full, o_empty, p_empty;
     __shared__ uint32_t tmem_slot;
     __shared__ float s_lsum[kRowSplit][AQ];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -89,6 +89,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
             mbar_init(&v_full, 1); mbar_init(&v_empty, 1);
             mbar_init(&s_full, 1); mbar_init(&o_full, 1);
             mbar_init(&p_full, kStatic ? 128 * kRowSplit : 128); mbar_init(&o_empty, 128); mbar_init(&p_empty, 1);
+            mbar_init(&s_empty, 128 * kRowSplit);
             fence_barrier_init();
         }
         __syncwarp();
@@ -139,8 +140,18 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
             issue_s(0);
             for (int j = 0; j < nb; j++) {
                 const uint32_t ph = j & 1;
-                mbar_wait(&p_full, ph);                 // P_j staged; S_j has been consumed
-                if (j + 1 < nb) issue_s(j + 1);         // next QK^T overlaps this block's P*V and the O read-out
+                if (kStatic) {
+                    // S_j is in the softmax threads' registers: the next QK^T runs under this block's exponentials
+                    if (j + 1 < nb) {
+                        mbar_wait(&s_empty, ph);
+                        tc_fence_after();
+                        issue_s(j + 1);
+                    }
+                    mbar_wait(&p_full, ph);                 // P_j staged
+                } else {
+                    mbar_wait(&p_full, ph);                 // P_j staged; S_j has been consumed
+                    if (j + 1 < nb) issue_s(j + 1);         // next QK^T overlaps this block's P*V and the O read-out
+                }
                 mbar_wait(&v_full, ph);
                 if (!kStatic) mbar_wait(&o_empty, ph ^ 1);   // softmax warps have read O_{j-1}
                 tc_fence_after();
@@ -192,27 +203,32 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
             const int part = (warp - 2) >> 2;
             float ls0 = 0.f, ls1 = 0.f, ls2 = 0.f, ls3 = 0.f;
             // P sub-tile (64 keys each) and first 16-byte chunk inside it
-            uint8_t *psub = prow + ((part * KP) >> 6) * (kPBytes / 2);
+            const uint32_t psub = smem_u32(prow) + ((part * KP) >> 6) * (kPBytes / 2);
             const int chunk0 = ((part * KP) & 63) >> 3;
             const uint32_t tS_mine = tS + lane_off + part * KP;
             for (int j = 0; j < nb; j++) {
                 mbar_wait(&s_full, j & 1);
                 tc_fence_after();
                 const int kbase = j * AK + part * KP;
-                const bool ragged = kbase + KP > Nk;
                 uint32_t r[KP / 32][32];
 #pragma unroll
                 for (int h2 = 0; h2 < KP / 32; h2++) tmem_ld_32x32b_x32(tS_mine + h2 * 32, r[h2]);   // all loads in flight
                 tmem_ld_wait();
+                tc_fence_before();
+                mbar_arrive(&s_empty);                       // S_j now lives in registers
+                if (kbase + KP > Nk) {                       // ragged last block only (warp-uniform): mask the padding keys
+#pragma unroll
+                    for (int h2 = 0; h2 < KP / 32; h2++)
+#pragma unroll
+                        for (int i = 0; i < 32; i++)
+                            if (kbase + h2 * 32 + i >= Nk) r[h2][i] = 0xff800000u;      // -inf
+                }
 #pragma unroll
                 for (int h2 = 0; h2 < KP / 32; h2++) {
                     // exponentials overwrite the score registers (keeps the live set at 32 values)
 #pragma unroll
-                    for (int i = 0; i < 32; i++) {
-                        float v = __uint_as_float(r[h2][i]);
-                        if (ragged && kbase + h2 * 32 + i >= Nk) v = -INFINITY;
-                        r[h2][i] = __float_as_uint(ex2_fast(fmaf(v, scale_log2, -bound_log2)));
-                    }
+                    for (int i = 0; i < 32; i++)
+                        r[h2][i] = __float_as_uint(ex2_fast(fmaf(__uint_as_float(r[h2][i]), scale_log2, -bound_log2)));
 #pragma unroll
                     for (int i = 0; i < 32; i += 4) {
                         ls0 += __uint_as_float(r[h2][i]); ls1 += __uint_as_float(r[h2][i + 1]);
@@ -220,14 +236,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
                     }
                     if (h2 == 0 && j > 0) mbar_wait(&p_empty, (j - 1) & 1);   // P*V of the previous block has retired
 #pragma unroll
-                    for (int g = 0; g < 4; g++) {
-                        const uint32_t *pp = &r[h2][8 * g];
-                        *reinterpret_cast<uint4 *>(psub + (((chunk0 + h2 * 4 + g) ^ (row & 7)) << 4)) =
-                            make_uint4(pack2(__uint_as_float(pp[0]), __uint_as_float(pp[1])),
-                                       pack2(__uint_as_float(pp[2]), __uint_as_float(pp[3])),
-                                       pack2(__uint_as_float(pp[4]), __uint_as_float(pp[5])),
-                                       pack2(__uint_as_float(pp[6]), __uint_as_float(pp[7])));
-                    }
+                    for (int g = 0; g < 4; g++)
+                        sts128(psub + (((chunk0 + h2 * 4 + g) ^ (row & 7)) << 4),
+                               pack2(__uint_as_float(r[h2][8 * g]), __uint_as_float(r[h2][8 * g + 1])),
+                               pack2(__uint_as_float(r[h2][8 * g + 2]), __uint_as_float(r[h2][8 * g + 3])),
+                               pack2(__uint_as_float(r[h2][8 * g + 4]), __uint_as_float(r[h2][8 * g + 5])),
+                               pack2(__uint_as_float(r[h2][8 * g + 6]), __uint_as_float(r[h2][8 * g + 7])));
                 }
                 fence_proxy_async_smem();
                 tc_fence_before();

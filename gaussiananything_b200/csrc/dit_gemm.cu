@@ -68,20 +68,6 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b)
 constexpr int kStageBytes = 4096;          // per epilogue warp
 constexpr int kHeadParams = 128;           // floats per epilogue warp: 64 bias + 64 norm weights (HEADS mode)
 
-// explicit shared-space accesses: through generic pointers the compiler could not prove that the staging loads
-// do not alias the global stores and serialised phase B load -> store -> load ...
-__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d)
-{
-    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d));
-}
-__device__ __forceinline__ uint4 lds128(uint32_t addr)
-{
-    uint4 v;
-    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];\n" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
-    return v;
-}
-__device__ __forceinline__ void warp_sync_smem() { asm volatile("bar.warp.sync 0xffffffff;\n" ::: "memory"); }
-
 __device__ __forceinline__ void stage_rows(uint32_t stg, int lane, const uint32_t (&r)[32])
 {
     const uint32_t row = stg + lane * 128;
@@ -306,6 +292,7 @@ template <int BN, int MODE>
 __device__ __forceinline__ void epilogue_tile(const GaGemmEpilogue &ep, uint32_t stg, float *hp, uint32_t trow, int lane,
                                               int chalf, int m0w, int n0, int M, int N)
 {
+    if (m0w >= M) return;                                          // warp-uniform: these 32 rows are padding
     if (MODE == GA_EPI_HEADS) {
 #pragma unroll 1
         for (int c = chalf * (BN / 2); c < (chalf + 1) * (BN / 2); c += 64)
