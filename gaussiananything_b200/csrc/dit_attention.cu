@@ -107,11 +107,18 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
         if (elect_one()) {
             mbar_expect_tx(&q_full, kQBytes);
             tma_load_2d(sQ, &tma_q, &q_full, 0, bh * pitch_q + q0);
-            for (int j = 0; j < nb; j++) {
+            // K runs one block ahead of V: its slot frees as soon as QK^T of block j-1 has retired, whereas the single
+            // V buffer frees only after P*V of block j-1 -- loading them in lock step delayed K_{j+1} (and with it
+            // S_{j+1}) past the end of block j's exponentials
+            auto load_k = [&](int j) {
                 const int s = j & 1;
                 mbar_wait(&k_empty[s], ((j >> 1) & 1) ^ 1);
                 mbar_expect_tx(&k_full[s], kKBytes);
                 tma_load_2d(sK + s * kKBytes, &tma_k, &k_full[s], 0, bh * pitch_k + j * AK);
+            };
+            load_k(0);
+            for (int j = 0; j < nb; j++) {
+                if (j + 1 < nb) load_k(j + 1);
                 mbar_wait(&v_empty, (j & 1) ^ 1);
                 mbar_expect_tx(&v_full, kVBytes);
                 tma_load_2d(sV, &tma_vt, &v_full, j * AK, bh * HD);
