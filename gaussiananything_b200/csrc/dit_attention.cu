@@ -17,6 +17,13 @@
 //              TMEM accumulated in registers with the running rescale.
 // Two CTAs share an SM (97 KB smem, 256 TMEM columns each), so one CTA's MMAs / TMA loads overlap
 // the other's softmax; within a CTA the next block's QK^T is issued as soon as S has been read.
+//
+// Static-bound path: P never touches shared memory.  With P staged in smem a key block moves 144 KB through the
+// SM's 128 B/clk shared-memory port (QK^T reads Q+K 32 KB, P*V reads P+V 48 KB, st.shared of P 32 KB, TMA fills
+// 32 KB) = 1150 cycles per CTA and block -- more than the 1024 cycles the MUFU pipe needs for the block's 16k
+// exponentials, and exactly the 2300 cycles per block pair tools/trace_attn.py measured.  The softmax threads now
+// write bf16 P straight into TMEM (tcgen05.st, 64 columns) and P*V takes its A operand from there
+// (tcgen05.mma [d], [a_tmem], b_desc): 80 KB per block, the kernel is MUFU-bound again.
 #include "../../include/ga_b200.h"
 #include "sm100_ptx.cuh"
 
@@ -24,6 +31,26 @@ using namespace sm100;
 
 int ga_make_tmap_bf16(CUtensorMap *map, const void *ptr, uint64_t rows, uint64_t cols, uint64_t ld_elems,
                       uint32_t box_rows);
+
+#ifdef GA_B200_TRACE
+// Debug build only (tools/trace_attn.py): per-CTA timeline of softmax warp 2 / the MMA thread, 8 stamps per key block.
+__device__ unsigned long long g_attn_trace[1024 * 160];
+#define ATRACE(slot) do { if (lane == 0) g_attn_trace[(blockIdx.y * gridDim.x + blockIdx.x) * 160 + (slot)] = clock64(); } while (0)
+#define ATRACE_BLK(j, e) do { if ((j) < 19) ATRACE(8 + (j) * 8 + (e)); } while (0)
+#define ATRACE_START() do { if (threadIdx.x == 64) { unsigned smid_; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid_)); \
+    g_attn_trace[(blockIdx.y * gridDim.x + blockIdx.x) * 160 + 0] = smid_; \
+    g_attn_trace[(blockIdx.y * gridDim.x + blockIdx.x) * 160 + 1] = clock64(); } } while (0)
+#define ATRACE_END() do { if (threadIdx.x == 64) g_attn_trace[(blockIdx.y * gridDim.x + blockIdx.x) * 160 + 2] = clock64(); } while (0)
+extern "C" int ga_debug_attn_trace(unsigned long long *host, int n)
+{
+    return (int)cudaMemcpyFromSymbol(host, g_attn_trace, sizeof(unsigned long long) * (size_t)n);
+}
+#else
+#define ATRACE(slot) do { } while (0)
+#define ATRACE_BLK(j, e) do { } while (0)
+#define ATRACE_START() do { } while (0)
+#define ATRACE_END() do { } while (0)
+#endif
 
 namespace {
 
@@ -99,7 +126,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = tmem_slot;
-    const uint32_t tS = tmem, tO = tmem + 128;
+    // columns: S 0-127 (fp32 scores) | static path: P 128-191 (bf16 pairs), O 192-255 | online path: O 128-191
+    const uint32_t tS = tmem, tP = tmem + 128, tO = kStatic ? tmem + 192 : tmem + 128;
+#ifdef GA_B200_TRACE
+    if (threadIdx.x == 64) {
+        unsigned smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        g_attn_trace[(blockIdx.y * gridDim.x + blockIdx.x) * 160 + 0] = smid;
+        g_attn_trace[(blockIdx.y * gridDim.x + blockIdx.x) * 160 + 1] = clock64();
+    }
+#endif
     pdl_wait();
     pdl_launch_dependents();
 
@@ -152,9 +187,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
                     if (j + 1 < nb) {
                         mbar_wait(&s_empty, ph);
                         tc_fence_after();
+                        if (j < 19) ATRACE(8 + j * 8 + 4);
                         issue_s(j + 1);
+                        if (j < 19) ATRACE(8 + j * 8 + 5);
                     }
                     mbar_wait(&p_full, ph);                 // P_j staged
+                    if (j < 19) ATRACE(8 + j * 8 + 6);
                 } else {
                     mbar_wait(&p_full, ph);                 // P_j staged; S_j has been consumed
                     if (j + 1 < nb) issue_s(j + 1);         // next QK^T overlaps this block's P*V and the O read-out
@@ -164,12 +202,19 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
                 tc_fence_after();
 #pragma unroll
                 for (int kk = 0; kk < AK / 16; kk++) {
-                    const uint64_t sub_p = (uint64_t)((kk >> 2) * ((kPBytes / 2) >> 4));
                     const uint64_t sub_v = (uint64_t)((kk >> 2) * ((kVBytes / 2) >> 4));
-                    umma_bf16_ss(tO, pd + sub_p + (uint64_t)(2 * (kk & 3)), vd + sub_v + (uint64_t)(2 * (kk & 3)),
-                                 idesc_o, kStatic ? (uint32_t)((j | kk) != 0) : (uint32_t)(kk != 0));
+                    if (kStatic) {
+                        // A = P from tensor memory: 16 keys = 8 columns per k-step
+                        umma_bf16_ts(tO, tP + (uint32_t)(kk * 8), vd + sub_v + (uint64_t)(2 * (kk & 3)), idesc_o,
+                                     (uint32_t)((j | kk) != 0));
+                    } else {
+                        const uint64_t sub_p = (uint64_t)((kk >> 2) * ((kPBytes / 2) >> 4));
+                        umma_bf16_ss(tO, pd + sub_p + (uint64_t)(2 * (kk & 3)), vd + sub_v + (uint64_t)(2 * (kk & 3)), idesc_o,
+                                     (uint32_t)(kk != 0));
+                    }
                 }
                 umma_commit(&v_empty);
+                if (kStatic && j < 19) ATRACE(8 + j * 8 + 7);
                 if (kStatic) {
                     umma_commit(&p_empty);                  // P (and V) may be overwritten
                     if (j == nb - 1) umma_commit(&o_full);  // O complete after the last key block
@@ -203,19 +248,20 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
             mbar_arrive(&o_empty);
         };
 
-        if (kStatic) {
+        if constexpr (kStatic) {
             // kRowSplit threads per query row: this one handles keys [part*KP, part*KP+KP) of every block; with no
             // running maximum the threads of a row never have to talk until the very end.
             constexpr int KP = AK / kRowSplit;                 // 32 or 64 keys per thread
             const int part = (warp - 2) >> 2;
             float ls0 = 0.f, ls1 = 0.f, ls2 = 0.f, ls3 = 0.f;
             // P sub-tile (64 keys each) and first 16-byte chunk inside it
-            const uint32_t psub = smem_u32(prow) + ((part * KP) >> 6) * (kPBytes / 2);
-            const int chunk0 = ((part * KP) & 63) >> 3;
             const uint32_t tS_mine = tS + lane_off + part * KP;
+            const uint32_t tP_mine = tP + lane_off + part * (KP / 2);          // two bf16 per column
+            static_assert(KP == 64, "one tcgen05.st.x32 per thread and block");
             for (int j = 0; j < nb; j++) {
                 mbar_wait(&s_full, j & 1);
                 tc_fence_after();
+                if (warp == 2 && j < 19) ATRACE(8 + j * 8 + 0);
                 const int kbase = j * AK + part * KP;
                 uint32_t r[KP / 32][32];
 #pragma unroll
@@ -223,6 +269,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
                 tmem_ld_wait();
                 tc_fence_before();
                 mbar_arrive(&s_empty);                       // S_j now lives in registers
+                if (warp == 2 && j < 19) ATRACE(8 + j * 8 + 1);
                 if (kbase + KP > Nk) {                       // ragged last block only (warp-uniform): mask the padding keys
 #pragma unroll
                     for (int h2 = 0; h2 < KP / 32; h2++)
@@ -230,9 +277,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
                         for (int i = 0; i < 32; i++)
                             if (kbase + h2 * 32 + i >= Nk) r[h2][i] = 0xff800000u;      // -inf
                 }
+                uint32_t pk[32];                             // this thread's 64 probabilities as bf16 pairs
 #pragma unroll
                 for (int h2 = 0; h2 < KP / 32; h2++) {
-                    // exponentials overwrite the score registers (keeps the live set at 32 values)
 #pragma unroll
                     for (int i = 0; i < 32; i++)
                         r[h2][i] = __float_as_uint(ex2_fast(fmaf(__uint_as_float(r[h2][i]), scale_log2, -bound_log2)));
@@ -241,18 +288,18 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
                         ls0 += __uint_as_float(r[h2][i]); ls1 += __uint_as_float(r[h2][i + 1]);
                         ls2 += __uint_as_float(r[h2][i + 2]); ls3 += __uint_as_float(r[h2][i + 3]);
                     }
-                    if (h2 == 0 && j > 0) mbar_wait(&p_empty, (j - 1) & 1);   // P*V of the previous block has retired
 #pragma unroll
-                    for (int g = 0; g < 4; g++)
-                        sts128(psub + (((chunk0 + h2 * 4 + g) ^ (row & 7)) << 4),
-                               pack2(__uint_as_float(r[h2][8 * g]), __uint_as_float(r[h2][8 * g + 1])),
-                               pack2(__uint_as_float(r[h2][8 * g + 2]), __uint_as_float(r[h2][8 * g + 3])),
-                               pack2(__uint_as_float(r[h2][8 * g + 4]), __uint_as_float(r[h2][8 * g + 5])),
-                               pack2(__uint_as_float(r[h2][8 * g + 6]), __uint_as_float(r[h2][8 * g + 7])));
+                    for (int i = 0; i < 16; i++)
+                        pk[h2 * 16 + i] = pack2(__uint_as_float(r[h2][2 * i]), __uint_as_float(r[h2][2 * i + 1]));
                 }
-                fence_proxy_async_smem();
+                if (warp == 2 && j < 19) ATRACE(8 + j * 8 + 2);
+                if (j > 0) mbar_wait(&p_empty, (j - 1) & 1); // P*V of the previous block has retired
+                tc_fence_after();
+                tmem_st_32x32b_x32(tP_mine, pk);
+                tmem_st_wait();
                 tc_fence_before();
                 mbar_arrive(&p_full);
+                if (warp == 2 && j < 19) ATRACE(8 + j * 8 + 3);
             }
             s_lsum[part][row] = (ls0 + ls1) + (ls2 + ls3);
             asm volatile("bar.sync 1, %0;\n" ::"n"(128 * kRowSplit) : "memory");      // the softmax warps only
@@ -359,11 +406,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
         }
     }
     __syncthreads();
+#ifdef GA_B200_TRACE
+    if (threadIdx.x == 64) g_attn_trace[(blockIdx.y * gridDim.x + blockIdx.x) * 160 + 2] = clock64();
+#endif
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc<kTmemColsAttn>(tmem);
     }
 }
+
 
 }  // namespace
 
@@ -374,6 +425,16 @@ extern "C" int ga_attention_bf16(const void *Q, const void *K, const void *Vt, v
     if (!Q || !K || !Vt || !out || batch <= 0 || heads <= 0 || Nq <= 0 || Nk <= 0) return GA_ERR_BADARG;
     if (pitch_q < Nq || pitch_k < Nk || pitch_k % 128 != 0) return GA_ERR_BADARG;
     const uint64_t BH = (uint64_t)batch * heads;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemAttn);
+        if (e != cudaSuccess) return (int)e;
+        e = cudaFuncSetAttribute(attn_fwd_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemAttn);
+        if (e != cudaSuccess) return (int)e;
+        attr_set = true;
+    }
+    // static-bound softmax only while exp(-2*bound) stays far from the fp32/bf16 underflow range
+    const bool use_static = score_bound > 0.f && score_bound <= 40.f;
     CUtensorMap tq, tk, tv;
     int rc = ga_make_tmap_bf16(&tq, Q, BH * pitch_q, HD, HD, AQ);
     if (rc) return rc;
@@ -381,31 +442,14 @@ extern "C" int ga_attention_bf16(const void *Q, const void *K, const void *Vt, v
     if (rc) return rc;
     rc = ga_make_tmap_bf16(&tv, Vt, BH * HD, (uint64_t)pitch_k, (uint64_t)pitch_k, HD);
     if (rc) return rc;
-    static bool attr_set = false;
-    static int split = 2;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemAttn);
-        if (e != cudaSuccess) return (int)e;
-        e = cudaFuncSetAttribute(attn_fwd_kernel<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemAttn);
-        if (e != cudaSuccess) return (int)e;
-        e = cudaFuncSetAttribute(attn_fwd_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemAttn);
-        if (e != cudaSuccess) return (int)e;
-        const char *sp = getenv("GA_B200_ATTN_SPLIT");
-        if (sp && sp[0] == '4') split = 4;
-        attr_set = true;
-    }
     dim3 grid((Nq + AQ - 1) / AQ, (unsigned)BH);
     const float log2e = 1.4426950408889634f;
     const float scale_log2 = softmax_scale * log2e;
-    // static-bound softmax only while exp(-2*bound) stays far from the fp32/bf16 underflow range
-    const bool use_static = score_bound > 0.f && score_bound <= 40.f;
     __nv_bfloat16 *o = reinterpret_cast<__nv_bfloat16 *>(out);
-    if (use_static && split == 4)
-        return (int)ga_launch_pdl(attn_fwd_kernel<true, 4>, grid, dim3(64 + 128 * 4), (size_t)kSmemAttn, (cudaStream_t)stream,
-                                  tq, tk, tv, o, Nq, Nk, pitch_q, pitch_k, heads, scale_log2, score_bound * log2e);
+    cudaStream_t st = (cudaStream_t)stream;
     if (use_static)
-        return (int)ga_launch_pdl(attn_fwd_kernel<true, 2>, grid, dim3(64 + 128 * 2), (size_t)kSmemAttn, (cudaStream_t)stream,
-                                  tq, tk, tv, o, Nq, Nk, pitch_q, pitch_k, heads, scale_log2, score_bound * log2e);
-    return (int)ga_launch_pdl(attn_fwd_kernel<false, 1>, grid, dim3(kAttnThreads), (size_t)kSmemAttn, (cudaStream_t)stream,
-                              tq, tk, tv, o, Nq, Nk, pitch_q, pitch_k, heads, scale_log2, 0.0f);
+        return (int)ga_launch_pdl(attn_fwd_kernel<true, 2>, grid, dim3(64 + 128 * 2), (size_t)kSmemAttn, st, tq, tk, tv, o, Nq,
+                                  Nk, pitch_q, pitch_k, heads, scale_log2, score_bound * log2e);
+    return (int)ga_launch_pdl(attn_fwd_kernel<false, 1>, grid, dim3(kAttnThreads), (size_t)kSmemAttn, st, tq, tk, tv, o, Nq, Nk,
+                              pitch_q, pitch_k, heads, scale_log2, 0.0f);
 }
