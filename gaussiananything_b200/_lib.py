@@ -39,6 +39,8 @@ def lib():
     for n in ("ga_raster_forward_bin", "ga_raster_forward_render"):
         getattr(L, n).argtypes = L.ga_raster_forward.argtypes
         getattr(L, n).restype = i32
+    L.ga_raster_forward_async.argtypes = L.ga_raster_forward.argtypes[:-1] + [vp, vp, vp]
+    L.ga_raster_forward_async.restype = i32
     L.ga_raster_backward_scratch_bytes.argtypes = [i32, i32, i32]
     L.ga_raster_backward_scratch_bytes.restype = sz
     L.ga_raster_backward.argtypes = [vp, i32, i32, i32, vp, vp, vp, i32, i32, f32,

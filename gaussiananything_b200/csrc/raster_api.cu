@@ -92,7 +92,7 @@ static int raster_forward_impl(int stage, const float *gauss13, int batch, int P
                                int H, int W, float scale_modifier,
                                float *out_color, float *out_allmap, int32_t *out_radii,
                                void *workspace, size_t workspace_bytes, int64_t max_instances,
-                               void *stream)
+                               void *stream, int32_t *status_host = nullptr, void *status_event = nullptr)
 {
     RasterDims d;
     int rc = make_dims(batch, P, views, H, W, scale_modifier, max_instances, &d);
@@ -112,7 +112,7 @@ static int raster_forward_impl(int stage, const float *gauss13, int batch, int P
         prof(0, s);
         if ((e = ga_launch_preprocess(d, w, gauss13, viewmats, projmats, out_radii, s)) != cudaSuccess) return (int)e;
         prof(1, s);
-        if ((e = ga_launch_binning(d, w, s)) != cudaSuccess) return (int)e;
+        if ((e = ga_launch_binning(d, w, s, status_host, (cudaEvent_t)status_event)) != cudaSuccess) return (int)e;
         prof(2, s);
     }
     if (stage == 0 || stage == 2) {
@@ -131,6 +131,19 @@ extern "C" int ga_raster_forward(const float *gauss13, int batch, int P, int vie
 {
     return raster_forward_impl(0, gauss13, batch, P, views, viewmats, projmats, bg, H, W, scale_modifier, out_color,
                                out_allmap, out_radii, workspace, workspace_bytes, max_instances, stream);
+}
+
+extern "C" int ga_raster_forward_async(const float *gauss13, int batch, int P, int views,
+                                       const float *viewmats, const float *projmats, const float *bg,
+                                       int H, int W, float scale_modifier,
+                                       float *out_color, float *out_allmap, int32_t *out_radii,
+                                       void *workspace, size_t workspace_bytes, int64_t max_instances,
+                                       int32_t *status_host, void *status_event, void *stream)
+{
+    if (!status_host || !status_event) return GA_ERR_BADARG;
+    return raster_forward_impl(0, gauss13, batch, P, views, viewmats, projmats, bg, H, W, scale_modifier, out_color,
+                               out_allmap, out_radii, workspace, workspace_bytes, max_instances, stream, status_host,
+                               status_event);
 }
 
 extern "C" int ga_raster_forward_bin(const float *gauss13, int batch, int P, int views,

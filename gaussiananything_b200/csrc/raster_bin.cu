@@ -236,9 +236,18 @@ sort_tiles_kernel(RasterDims d, RasterWs ws)
     }
 }
 
-cudaError_t ga_launch_binning(const RasterDims &d, const RasterWs &w, cudaStream_t s)
+cudaError_t ga_launch_binning(const RasterDims &d, const RasterWs &w, cudaStream_t s, int32_t *status_host,
+                              cudaEvent_t status_event)
 {
     scan_tiles_kernel<<<1, SCAN_THREADS, 0, s>>>(d, w);
+    if (status_host) {
+        cudaError_t e = cudaMemcpyAsync(status_host, w.status, 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, s);
+        if (e != cudaSuccess) return e;
+    }
+    if (status_event) {
+        cudaError_t e = cudaEventRecord(status_event, s);
+        if (e != cudaSuccess) return e;
+    }
     dim3 grid((d.P + 255) / 256, d.NV);
     scatter_kernel<<<grid, 256, 0, s>>>(d, w);
     sort_tiles_warp_kernel<<<(d.NV * d.T + 7) / 8, 256, 0, s>>>(d, w);

@@ -45,7 +45,11 @@ struct RasterWs {
 cudaError_t ga_launch_preprocess(const RasterDims &d, const RasterWs &w, const float *gauss13,
                                  const float *viewmats, const float *projmats,
                                  int32_t *out_radii, cudaStream_t s);
-cudaError_t ga_launch_binning(const RasterDims &d, const RasterWs &w, cudaStream_t s);
+// status_host / status_event (both optional): after the tile scan -- the first point where the instance count and
+// the overflow flag are known -- status[0..3] is copied to pinned host memory and the event recorded, so the host
+// can look at them while the scatter / sort / composite kernels are still running.
+cudaError_t ga_launch_binning(const RasterDims &d, const RasterWs &w, cudaStream_t s, int32_t *status_host = nullptr,
+                              cudaEvent_t status_event = nullptr);
 cudaError_t ga_launch_render_fwd(const RasterDims &d, const RasterWs &w, const float *bg,
                                  float *out_color, float *out_allmap, cudaStream_t s);
 cudaError_t ga_launch_render_bwd(const RasterDims &d, const RasterWs &w, const float *bg,

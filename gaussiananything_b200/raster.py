@@ -49,6 +49,21 @@ def workspace_views(ws, L, batch, P, views, H, W, max_instances):
     )
 
 
+_status_slots = {}
+
+
+def _status_slot(dev):
+    """Per-device pinned 4-int buffer + event for the overlapped status read-back of ga_raster_forward_async."""
+    key = (dev.type, dev.index if dev.index is not None else torch.cuda.current_device())
+    slot = _status_slots.get(key)
+    if slot is None:
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(dev))          # materialises the underlying cudaEvent_t
+        slot = (torch.zeros(4, dtype=torch.int32).pin_memory(), ev)
+        _status_slots[key] = slot
+    return slot
+
+
 def forward_raw(gauss13, viewmats, projmats, bg, H, W, scale_modifier=1.0, max_instances=None):
     """gauss13 [B,P,13], viewmats/projmats [B,V,4,4] (reference layout), bg [3].
     Returns (color [B,V,3,H,W], allmap [B,V,7,H,W], radii [B,V,P], state)."""
@@ -69,17 +84,21 @@ def forward_raw(gauss13, viewmats, projmats, bg, H, W, scale_modifier=1.0, max_i
     color = torch.empty(B, V, 3, H, W, device=dev, dtype=torch.float32)
     allmap = torch.empty(B, V, 7, H, W, device=dev, dtype=torch.float32)
     radii = torch.empty(B, V, P, device=dev, dtype=torch.int32)
+    host_status, ev = _status_slot(dev)
     while True:
         L = layout(B, P, V, H, W, max_instances)
         ws = torch.empty(L.total_bytes, device=dev, dtype=torch.uint8)
-        args = (_ptr(gauss13), B, P, V, _ptr(viewmats), _ptr(projmats), _ptr(bg), H, W, float(scale_modifier),
-                _ptr(color), _ptr(allmap), _ptr(radii), _ptr(ws), L.total_bytes, max_instances, _stream(dev))
-        _lib.check(lib.ga_raster_forward_bin(*args), "ga_raster_forward_bin")
-        # one small device->host read after the binning (where upstream reads num_rendered back); the composite is
-        # enqueued afterwards, so the GPU keeps working while the host goes on to enqueue whatever follows
-        status = ws[L.status:L.status + 64].view(torch.int32).cpu()
+        # the whole forward is enqueued in one call; the instance count / overflow flag (where upstream reads
+        # num_rendered back) is copied to pinned memory right after the tile scan, so this wait returns while the
+        # GPU is still scattering, sorting and compositing -- no bubble in the stream
+        _lib.check(lib.ga_raster_forward_async(
+            _ptr(gauss13), B, P, V, _ptr(viewmats), _ptr(projmats), _ptr(bg), H, W, float(scale_modifier),
+            _ptr(color), _ptr(allmap), _ptr(radii), _ptr(ws), L.total_bytes, max_instances,
+            C.c_void_p(host_status.data_ptr()), C.c_void_p(ev.cuda_event), _stream(dev)),
+            "ga_raster_forward_async")
+        ev.synchronize()
+        status = host_status.clone()
         if int(status[1]) == 0:
-            _lib.check(lib.ga_raster_forward_render(*args), "ga_raster_forward_render")
             break
         max_instances = int(int(status[0]) * 1.25) + 1024
         _capacity_hint[key] = max_instances

@@ -88,6 +88,18 @@ int ga_raster_forward_render(const float *gauss13, int batch, int P, int views,
                              float *out_color, float *out_allmap, int32_t *out_radii,
                              void *workspace, size_t workspace_bytes, int64_t max_instances, void *stream);
 
+/* The whole forward enqueued at once, with the status read-back overlapped: right after the tile scan (before the
+ * scatter, the sort and the composite) status[0..3] = {instance count, overflow flag, tiles sorted in global memory,
+ * 0} is copied to `status_host` (pinned host memory, 4 ints) and `status_event` (a cudaEvent_t) is recorded.  The
+ * caller synchronises on the event -- the GPU is still busy with the rest of the forward -- and, if the overflow
+ * flag is set, re-runs with a larger workspace (the kernels after the scan exit early in that case). */
+int ga_raster_forward_async(const float *gauss13, int batch, int P, int views,
+                            const float *viewmats, const float *projmats, const float *bg,
+                            int H, int W, float scale_modifier,
+                            float *out_color, float *out_allmap, int32_t *out_radii,
+                            void *workspace, size_t workspace_bytes, int64_t max_instances,
+                            int32_t *status_host, void *status_event, void *stream);
+
 /* Post-processing of /root/reference/nsr/gs_surfel.py:121-163 for all views at once: image = clamp(color,0,1),
  * alpha = allmap[1], depth = nan_to_num(allmap[5], 0, 0), normal[d] = sum_c allmap[2+c] * view[d][c], dist = allmap[6].
  * color [NV,3,H,W], allmap [NV,7,H,W], viewmats [NV,16] (as passed to the rasteriser); outputs contiguous. */
