@@ -23,12 +23,12 @@ constexpr int kEpiWarps = 8;
 constexpr int kThreads = 64 + 32 * kEpiWarps;          // TMA warp + MMA warp + 8 epilogue warps
 
 template <int BN> struct GemmCfg {
-    static constexpr int kStages = (BN >= 256) ? 3 : (BN >= 128 ? 5 : 7);      // + 36 KB of epilogue staging
+    static constexpr int kStages = (BN >= 256) ? 3 : (BN >= 192 ? 4 : (BN >= 128 ? 5 : 7));    // + 36 KB of epilogue staging
     static constexpr int kABytes = BM * BK * 2;
     static constexpr int kBBytes = BN * BK * 2;
     static constexpr int kRing = kStages * (kABytes + kBBytes);
     static constexpr int kSmem = kRing + 1024 + 36 * 1024;
-    static constexpr int kTmemCols = 2 * BN;           // double-buffered accumulator
+    static constexpr int kTmemCols = (2 * BN <= 128) ? 128 : (2 * BN <= 256 ? 256 : 512);     // double-buffered accumulator (power of two)
 };
 
 // exact-erf GELU to ~3e-7 (Abramowitz-Stegun 7.1.28: erf x = 1 - (1 + a1 x + .. + a6 x^6)^-16), 1 MUFU + ~16 FP32
@@ -655,7 +655,8 @@ static int launch_gemm(const void *A, int lda, const void *W, int ldw, const GaG
     case GA_EPI_F32: return launch_gemm_mode<BN, CS, GA_EPI_F32>(ta, tb, ep, M, N, K, s);
     case GA_EPI_RESID_GATE_F32: return launch_gemm_mode<BN, CS, GA_EPI_RESID_GATE_F32>(ta, tb, ep, M, N, K, s);
     case GA_EPI_HEADS:
-        if (BN >= 128) return launch_gemm_mode<(BN >= 128 ? BN : 128), CS, GA_EPI_HEADS>(ta, tb, ep, M, N, K, s);
+        if (BN == 128 || BN == 256)
+            return launch_gemm_mode<((BN == 128 || BN == 256) ? BN : 128), CS, GA_EPI_HEADS>(ta, tb, ep, M, N, K, s);
         return GA_ERR_BADARG;
     default: return GA_ERR_BADARG;
     }
@@ -708,11 +709,13 @@ extern "C" int ga_gemm_bf16_tn(const void *A, int lda, const void *W, int ldw, i
     const int cs = block_n >= 1000 ? block_n / 1000 : 1;
     const int bn = block_n % 1000;
     if (epi->mode == GA_EPI_HEADS && (N % 64 != 0 || epi->heads <= 0 || bn < 128)) return GA_ERR_BADARG;
-    if (bn != 64 && bn != 128 && bn != 256) return GA_ERR_BADARG;
+    if (bn != 64 && bn != 128 && bn != 192 && bn != 256) return GA_ERR_BADARG;
+    if (bn == 192 && (cs != 1 || epi->mode == GA_EPI_HEADS)) return GA_ERR_BADARG;        // 96 columns per epilogue warp: no whole heads
     cudaStream_t s = (cudaStream_t)stream;
     if (cs == 1) {
         if (bn == 64) return launch_gemm<64, 1>(A, lda, W, ldw, *epi, M, N, K, s);
         if (bn == 128) return launch_gemm<128, 1>(A, lda, W, ldw, *epi, M, N, K, s);
+        if (bn == 192) return launch_gemm<192, 1>(A, lda, W, ldw, *epi, M, N, K, s);
         return launch_gemm<256, 1>(A, lda, W, ldw, *epi, M, N, K, s);
     }
     if (cs == 2) {

@@ -76,19 +76,25 @@ def _ck(rc, what):
 _GEMM_CFG_ENV = None
 
 
-def _gemm_config(M, N):
-    """Tile width + 1000 * cluster size (ga_b200.h).  Measured on B200 (tools/sweep_gemm.py, profiles/r01_gemm_sweep.txt):
-    128x128 tiles without clusters win on every DiT shape -- the main loop is limited by each SM's own operand
-    ingest, which TMA multicast does not reduce (only cta_group::2 MMA would).  GA_B200_GEMM_CFG overrides."""
+def _gemm_config(M, N, mode=None):
+    """Tile width (+ 1000 * cluster size, ga_b200.h).  Measured on B200 (tools/sweep_gemm.py,
+    profiles/r01_gemm_sweep.txt): the main loop is bound by the SM's shared-memory port (operand reads + TMA fills), so
+    wider tiles are more efficient per byte, but only pay when the tile count still fills the 148 SMs evenly.
+    128 x 128 is the default; the residual-update GEMMs with N = 768 (192 tiles of 128 x 128 = 1.3 waves) run as
+    128 tiles of 128 x 192 in a single wave: 14.6 -> 12.7 us (K = 768), 25.9 -> 21.8 us (K = 3072).
+    GA_B200_GEMM_CFG="big,small" overrides."""
     global _GEMM_CFG_ENV
     if _GEMM_CFG_ENV is None:
         import os
         _GEMM_CFG_ENV = os.environ.get("GA_B200_GEMM_CFG", "")
     if _GEMM_CFG_ENV:
         big, small = (int(v) for v in _GEMM_CFG_ENV.split(","))
-    else:
-        big, small = 128, 128
-    return big if (M >= 1024 and N >= 512) else small
+        return big if (M >= 1024 and N >= 512) else small
+    tiles128 = -(-M // 128) * -(-N // 128)
+    tiles192 = -(-M // 128) * -(-N // 192)
+    if mode == EPI_RESID_GATE_F32 and N % 192 == 0 and tiles128 > 148 and tiles192 <= 148:
+        return 192
+    return 128
 
 
 def _round_up(x, m):
@@ -385,7 +391,7 @@ class _DiTEngine:
     # ---- launches
     def _gemm(self, A, W, M, N, K, epi, st, bn=None):
         if bn is None:
-            bn = _gemm_config(M, N)
+            bn = _gemm_config(M, N, epi.mode)
         _ck(self.L.ga_gemm_bf16_tn(_p(A), K, _p(W), K, M, N, K, C.byref(epi), bn, st), "ga_gemm_bf16_tn")
 
     def _epi(self, mode, **kw):

@@ -169,7 +169,7 @@ typedef struct GaGemmEpilogue {
 } GaGemmEpilogue;
 
 /* A [M, lda] bf16 row-major, W [N, ldw] bf16 row-major (nn.Linear weight), K contiguous in both.
- * block_n = tile width {64, 128, 256} (the 128 x width output tile) + 1000 * cluster size {1, 2}: a cluster of
+ * block_n = tile width {64, 128, 192, 256} (the 128 x width output tile; 192: not for GA_EPI_HEADS) + 1000 * cluster size {1, 2}: a cluster of
  * CTAs on vertically adjacent tiles shares the W tile through TMA multicast (e.g. 4256 = width 256, cluster 4);
  * 9000 + width {128, 256} = CTA pair (tcgen05 cta_group::2) computing a 256 x width tile.
  * lda, ldw multiples of 8. */

@@ -37,7 +37,8 @@ def _gemm(dit, L, st, A, W, epi, bn):
 
 
 @pytest.mark.parametrize("M,N,K,bn", [(128, 128, 64, 128), (128, 64, 16, 64), (256, 256, 256, 128),
-                                      (1000, 768, 768, 128), (4096, 3072, 768, 256), (200, 192, 1024, 64)])
+                                      (1000, 768, 768, 128), (4096, 3072, 768, 256), (200, 192, 1024, 64),
+                                      (4096, 768, 3072, 192), (300, 500, 136, 192)])
 def test_gemm_bias_bf16(M, N, K, bn):
     dit, L, dev, st = _env()
     torch.manual_seed(M + N + K)
@@ -78,6 +79,13 @@ def test_gemm_epilogues():
                                                  gate=gate.data_ptr(), gate_ld=6 * D, rows_per_batch=Ntok), 128)
     want = x0 + gate.repeat_interleave(Ntok, 0) * ref[:, :D]
     assert rel(x, want) < 1e-5
+    # the same with 128 x 192 tiles (the width the engine picks for the N = 768 residual GEMMs); 192 has no HEADS mode
+    x = x0.clone()
+    _gemm(dit, L, st, A, Wd, dit.GaGemmEpilogue(mode=dit.EPI_RESID_GATE_F32, bias=bias.data_ptr(), out=x.data_ptr(), ld_out=D,
+                                                 gate=gate.data_ptr(), gate_ld=6 * D, rows_per_batch=Ntok), 192)
+    assert rel(x, want) < 1e-5
+    bad = dit.GaGemmEpilogue(mode=dit.EPI_HEADS, heads=H)
+    assert L.ga_gemm_bf16_tn(dit._p(A), K, dit._p(W), K, M, 3 * D, K, C.byref(bad), 192, st) != 0
     # heads: q,k normed + v transposed
     Np = 256
     W3 = W[:3 * D].contiguous()

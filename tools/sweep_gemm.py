@@ -13,7 +13,7 @@ dev = torch.device("cuda:0")
 st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
 shapes = [(4096, 768, 768), (4096, 2304, 768), (4096, 3072, 768), (4096, 768, 3072),
           (1536, 1024, 1024), (1536, 3072, 1024), (1536, 4096, 1024), (1536, 1024, 4096), (2738, 1536, 1024)]
-cfgs = [64, 128, 256, 9128, 9256]
+cfgs = [64, 128, 192, 256, 9128]
 MODE = dit.EPI_GELU_BF16 if "gelu" in sys.argv else (dit.EPI_RESID_GATE_F32 if "resid" in sys.argv else dit.EPI_BF16)
 for (M, N, K) in shapes:
     torch.manual_seed(0)
