@@ -76,144 +76,11 @@ __device__ __forceinline__ bool eval_pair(const float4 a, const float4 b, const 
 //  f0 = C.x C.y C.z A.x | f1 = A.y A.z B.x B.y | f2 = B.z Tw.x Tw.y Tw.z
 //  f3 = xy.x-o.x xy.y-o.y opacity - | f4 = cull box (tile-local x0 x1 y0 y1)
 //  f5 = n.x n.y n.z r | f6 = g b - -
+// warp-uniform surfel iteration (every lane evaluates the same surfel).  A variant in which every lane walks its own
+// stream of hits needed 40 % fewer evaluation rounds but lost them again to non-broadcast shared-memory reads
+// (0.208 vs 0.199 ms): removed, see DESIGN.md.
 __global__ void __launch_bounds__(256)
 render_fwd_kernel(RasterDims d, RasterWs ws, const float *__restrict__ bg,
-                  float *__restrict__ out_color, float *__restrict__ out_allmap)
-{
-    __shared__ float4 s_rec[7][CHUNK];
-    if (ws.status[1]) return;
-    const int view = blockIdx.z;
-    const int tile = blockIdx.y * d.gx + blockIdx.x;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int ox = blockIdx.x * GA_BLOCK_X, oy = blockIdx.y * GA_BLOCK_Y;
-    const int lx0 = (warp & 1) * 8, ly0 = (warp >> 1) * 4;       // warp's 8x4 block, tile-local
-    const int lxi = lx0 + (lane & 7), lyi = ly0 + (lane >> 3);
-    const int pxi = ox + lxi, pyi = oy + lyi;
-    const bool inside = pxi < d.W && pyi < d.H;
-    const float dxf = (float)lxi, dyf = (float)lyi;
-    const float bx_lo = (float)lx0, bx_hi = (float)(lx0 + 7);
-    const float by_lo = (float)ly0, by_hi = (float)(ly0 + 3);
-    const float oxf = (float)ox, oyf = (float)oy;
-
-    const uint32_t start = ws.tile_start[(size_t)view * d.T + tile];
-    const uint32_t end = ws.tile_start[(size_t)view * d.T + tile + 1];
-    const int total = (int)(end - start);
-    const float *rec_base = ws.rec + (size_t)view * d.P * GA_REC_F;
-
-    bool done = !inside;
-    float T = 1.0f, C0 = 0, C1 = 0, C2 = 0, N0 = 0, N1 = 0, N2 = 0;
-    float Dacc = 0, M1 = 0, M2 = 0, dist = 0, median_depth = 0;
-    int last_contributor = 0, median_contributor = -1;
-
-    for (int c0 = 0; c0 < total; c0 += CHUNK) {
-        if (__syncthreads_count(done) == 256) break;
-        const int cnt = min(CHUNK, total - c0);
-        if ((int)threadIdx.x < cnt) {
-            const uint32_t id = ws.ids[start + c0 + threadIdx.x];
-            const float4 *src = reinterpret_cast<const float4 *>(rec_base + (size_t)id * GA_REC_F);
-            const float4 a = __ldg(src), b = __ldg(src + 1), c = __ldg(src + 2);
-            const float4 nr = __ldg(src + 3), bb = __ldg(src + 4), gb = __ldg(src + 5);
-            // Tu = a.xyz, Tv = (a.w,b.x,b.y), Tw = (b.z,b.w,c.x), xy = (c.y,c.z), opacity = c.w
-            const float k0 = oxf * b.z - a.x, k1 = oxf * b.w - a.y, k2 = oxf * c.x - a.z;
-            const float l0 = oyf * b.z - a.w, l1 = oyf * b.w - b.x, l2 = oyf * c.x - b.y;
-            const float Cx = k1 * l2 - k2 * l1, Cy = k2 * l0 - k0 * l2, Cz = k0 * l1 - k1 * l0;
-            const float Ax = b.w * l2 - c.x * l1, Ay = c.x * l0 - b.z * l2, Az = b.z * l1 - b.w * l0;
-            const float Bx = k1 * c.x - k2 * b.w, By = k2 * b.z - k0 * c.x, Bz = k0 * b.w - k1 * b.z;
-            s_rec[0][threadIdx.x] = make_float4(Cx, Cy, Cz, Ax);
-            s_rec[1][threadIdx.x] = make_float4(Ay, Az, Bx, By);
-            s_rec[2][threadIdx.x] = make_float4(Bz, b.z, b.w, c.x);
-            s_rec[3][threadIdx.x] = make_float4(c.y - oxf, c.z - oyf, c.w, 0.f);
-            s_rec[4][threadIdx.x] = make_float4(bb.x - oxf, bb.y - oxf, bb.z - oyf, bb.w - oyf);
-            s_rec[5][threadIdx.x] = nr;
-            s_rec[6][threadIdx.x] = gb;
-        }
-        __syncthreads();
-        for (int g0 = 0; g0 < cnt; g0 += 32) {
-            if (__all_sync(0xffffffffu, done)) break;
-            // level 1: which of these 32 surfels can touch this warp's 8x4 block at all
-            const int j = g0 + lane;
-            bool hit = false;
-            if (j < cnt) {
-                const float4 bb = s_rec[4][j];
-                hit = !(bb.y < bx_lo || bb.x > bx_hi || bb.w < by_lo || bb.z > by_hi);
-            }
-            unsigned mask = __ballot_sync(0xffffffffu, hit);
-            // level 2: per-lane stream = the hits whose cull box contains THIS pixel.  Each lane then walks its
-            // own stream (in list order, so compositing order is unchanged); lanes evaluate different surfels
-            // in the same instruction, which roughly halves the number of evaluation rounds.
-            unsigned mine = 0;
-            while (mask) {
-                const int b = __ffs(mask) - 1;
-                mask &= mask - 1;
-                const float4 bb = s_rec[4][g0 + b];
-                if (dxf >= bb.x && dxf <= bb.y && dyf >= bb.z && dyf <= bb.w) mine |= 1u << b;
-            }
-            if (done) mine = 0;
-            while (__any_sync(0xffffffffu, mine != 0)) {
-                const bool active = mine != 0;
-                const int jj = g0 + (active ? __ffs(mine) - 1 : 0);
-                mine &= mine - 1;
-                const float4 f0 = s_rec[0][jj], f1 = s_rec[1][jj], f2 = s_rec[2][jj], f3 = s_rec[3][jj];
-                const float p0 = f0.x + dxf * f0.w + dyf * f1.z;
-                const float p1 = f0.y + dxf * f1.x + dyf * f1.w;
-                const float p2 = f0.z + dxf * f1.y + dyf * f2.x;
-                const float ip = fast_rcp(p2);
-                const float s0 = p0 * ip, s1 = p1 * ip;
-                const float rho3d = s0 * s0 + s1 * s1;
-                const float ddx = f3.x - dxf, ddy = f3.y - dyf;
-                const float rho2d = GA_FILTER_INV_SQUARE * (ddx * ddx + ddy * ddy);
-                const float rho = fminf(rho3d, rho2d);
-                const float depth = (rho3d <= rho2d) ? (s0 * f2.y + s1 * f2.z) + f2.w : f2.w;
-                // power = -0.5*rho > 0 never happens for rho >= 0; NaN rho (p2 == 0) fails the alpha test
-                const float alpha = fminf(0.99f, f3.z * fast_ex2(rho * GA_NEG_HALF_LOG2E));
-                bool ok = active && p2 != 0.0f && depth >= GA_NEAR_N && alpha >= 1.0f / 255.0f;
-                if (ok) {
-                    const float test_T = T * (1 - alpha);
-                    if (test_T < 0.0001f) {
-                        done = true;
-                        mine = 0;
-                    } else {
-                        const float4 nr = s_rec[5][jj], gb = s_rec[6][jj];
-                        const int contributor = c0 + jj + 1;
-                        const float w = alpha * T;
-                        const float A = 1 - T;
-                        const float m = GA_M_C0 - GA_M_C1 * fast_rcp(depth);
-                        dist += (m * m * A + M2 - 2 * m * M1) * w;
-                        Dacc += depth * w;
-                        M1 += m * w;
-                        M2 += m * m * w;
-                        if (T > 0.5f) { median_depth = depth; median_contributor = contributor; }
-                        N0 += nr.x * w; N1 += nr.y * w; N2 += nr.z * w;
-                        C0 += nr.w * w; C1 += gb.x * w; C2 += gb.y * w;
-                        T = test_T;
-                        last_contributor = contributor;
-                    }
-                }
-            }
-        }
-        __syncthreads();
-    }
-    if (inside) {
-        const size_t HW = (size_t)d.H * d.W;
-        const size_t pix = (size_t)pyi * d.W + pxi;
-        float *fT = ws.final_T + (size_t)view * 3 * HW;
-        int32_t *nc = ws.n_contrib + (size_t)view * 2 * HW;
-        fT[pix] = T; fT[pix + HW] = M1; fT[pix + 2 * HW] = M2;
-        nc[pix] = last_contributor; nc[pix + HW] = median_contributor;
-        float *oc = out_color + (size_t)view * 3 * HW;
-        oc[pix] = C0 + T * bg[0]; oc[pix + HW] = C1 + T * bg[1]; oc[pix + 2 * HW] = C2 + T * bg[2];
-        float *oa = out_allmap + (size_t)view * 7 * HW;
-        oa[pix] = Dacc;
-        oa[pix + HW] = 1 - T;
-        oa[pix + 2 * HW] = N0; oa[pix + 3 * HW] = N1; oa[pix + 4 * HW] = N2;
-        oa[pix + 5 * HW] = median_depth;
-        oa[pix + 6 * HW] = dist;
-    }
-}
-
-// v2: warp-uniform surfel iteration (every lane evaluates the same surfel)
-__global__ void __launch_bounds__(256)
-render_fwd_kernel_v2(RasterDims d, RasterWs ws, const float *__restrict__ bg,
                   float *__restrict__ out_color, float *__restrict__ out_allmap)
 {
     __shared__ float4 s_rec[7][CHUNK];
@@ -339,10 +206,7 @@ cudaError_t ga_launch_render_fwd(const RasterDims &d, const RasterWs &w, const f
                                  float *out_color, float *out_allmap, cudaStream_t s)
 {
     dim3 grid(d.gx, d.gy, d.NV);
-    static int variant = -1;
-    if (variant < 0) { const char *e = getenv("GA_B200_FWD"); variant = (e && e[0] == '3') ? 3 : 2; }
-    if (variant == 3) render_fwd_kernel<<<grid, 256, 0, s>>>(d, w, bg, out_color, out_allmap);
-    else render_fwd_kernel_v2<<<grid, 256, 0, s>>>(d, w, bg, out_color, out_allmap);
+    render_fwd_kernel<<<grid, 256, 0, s>>>(d, w, bg, out_color, out_allmap);
     return cudaGetLastError();
 }
 
@@ -681,227 +545,6 @@ render_bwd_kernel(RasterDims d, RasterWs ws, const float *__restrict__ bg,
     }
 }
 
-// v2: per-(warp, surfel) recursive-halving reduction + shared-memory accumulators
-__device__ __forceinline__ float warp_sum(float v)
-{
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
-
-__global__ void __launch_bounds__(256)
-render_bwd_kernel_v2(RasterDims d, RasterWs ws, const float *__restrict__ bg,
-                  const float *__restrict__ dL_dcolor, const float *__restrict__ dL_dallmap,
-                  float *__restrict__ grad_acc)
-{
-    __shared__ float4 s_rec[6][CHUNK];
-    __shared__ float s_acc[CHUNK][GA_GRAD_F + 1];
-    __shared__ uint32_t s_id[CHUNK];
-    __shared__ int s_touched[CHUNK];
-    __shared__ int s_maxc;
-    if (ws.status[1]) return;
-    const int view = blockIdx.z;
-    const int tile = blockIdx.y * d.gx + blockIdx.x;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int wx0 = blockIdx.x * GA_BLOCK_X + (warp & 1) * 8;
-    const int wy0 = blockIdx.y * GA_BLOCK_Y + (warp >> 1) * 4;
-    const int pxi = wx0 + (lane & 7), pyi = wy0 + (lane >> 3);
-    const bool inside = pxi < d.W && pyi < d.H;
-    const float pfx = (float)pxi, pfy = (float)pyi;
-    const float bx_lo = (float)wx0, bx_hi = (float)(wx0 + 7);
-    const float by_lo = (float)wy0, by_hi = (float)(wy0 + 3);
-
-    const uint32_t start = ws.tile_start[(size_t)view * d.T + tile];
-    const size_t HW = (size_t)d.H * d.W;
-    const size_t pix = inside ? (size_t)pyi * d.W + pxi : 0;
-    const float *fT = ws.final_T + (size_t)view * 3 * HW;
-    const int32_t *nc = ws.n_contrib + (size_t)view * 2 * HW;
-    const float *rec_base = ws.rec + (size_t)view * d.P * GA_REC_F;
-    float *acc_base = grad_acc + (size_t)view * d.P * GA_GRAD_F;
-
-    const float T_final = inside ? fT[pix] : 0.f;
-    float T = T_final;
-    const int last_contributor = inside ? nc[pix] : 0;
-    const int median_contributor = inside ? nc[pix + HW] : 0;
-    float dpx0 = 0, dpx1 = 0, dpx2 = 0, dL_ddepth = 0, dL_daccum = 0, dL_dreg = 0;
-    float dn0 = 0, dn1 = 0, dn2 = 0, dL_dmedian = 0;
-    if (inside) {
-        const float *gc = dL_dcolor + (size_t)view * 3 * HW;
-        const float *ga = dL_dallmap + (size_t)view * 7 * HW;
-        dpx0 = gc[pix]; dpx1 = gc[pix + HW]; dpx2 = gc[pix + 2 * HW];
-        dL_ddepth = ga[pix]; dL_daccum = ga[pix + HW];
-        dn0 = ga[pix + 2 * HW]; dn1 = ga[pix + 3 * HW]; dn2 = ga[pix + 4 * HW];
-        dL_dmedian = ga[pix + 5 * HW]; dL_dreg = ga[pix + 6 * HW];
-    }
-    const float final_D = inside ? fT[pix + HW] : 0.f, final_D2 = inside ? fT[pix + 2 * HW] : 0.f;
-    const float final_A = 1 - T_final;
-    const float bg_dot_dpixel = bg[0] * dpx0 + bg[1] * dpx1 + bg[2] * dpx2;
-    float ar0 = 0, ar1 = 0, ar2 = 0, lc0 = 0, lc1 = 0, lc2 = 0;
-    float last_alpha = 0, last_depth = 0, ln0 = 0, ln1 = 0, ln2 = 0;
-    float accum_depth_rec = 0, accum_alpha_rec = 0, an0 = 0, an1 = 0, an2 = 0, last_dL_dT = 0;
-
-    // nothing behind the deepest contributor of the tile can receive gradient
-    if (threadIdx.x == 0) s_maxc = 0;
-    __syncthreads();
-    {
-        int m = last_contributor;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
-        if (lane == 0) atomicMax(&s_maxc, m);
-    }
-    __syncthreads();
-    const int total = s_maxc;          // list positions [0,total) matter
-
-    for (int hi = total; hi > 0; hi -= CHUNK) {
-        const int lo = max(0, hi - CHUNK);
-        const int cnt = hi - lo;
-        // stage positions lo..hi-1; slot t holds position hi-1-t (back to front)
-        if ((int)threadIdx.x < cnt) {
-            const uint32_t id = ws.ids[start + (hi - 1 - threadIdx.x)];
-            s_id[threadIdx.x] = id;
-            const float4 *src = reinterpret_cast<const float4 *>(rec_base + (size_t)id * GA_REC_F);
-#pragma unroll
-            for (int q = 0; q < 6; q++) s_rec[q][threadIdx.x] = __ldg(src + q);
-#pragma unroll
-            for (int f = 0; f < GA_GRAD_F; f++) s_acc[threadIdx.x][f] = 0.f;
-            s_touched[threadIdx.x] = 0;
-        }
-        __syncthreads();
-        for (int g0 = 0; g0 < cnt; g0 += 32) {
-            const int j = g0 + lane;
-            bool hit = false;
-            if (j < cnt) {
-                const float4 bb = s_rec[4][j];
-                hit = !(bb.y < bx_lo || bb.x > bx_hi || bb.w < by_lo || bb.z > by_hi);
-            }
-            unsigned mask = __ballot_sync(0xffffffffu, hit);
-            while (mask) {
-                const int jj = g0 + __ffs(mask) - 1;
-                mask &= mask - 1;
-                const int contributor = hi - 1 - jj;       // 0-based list position
-                const float4 a = s_rec[0][jj], b = s_rec[1][jj], c = s_rec[2][jj];
-                PixelGeom pg;
-                float k0, k1, k2, l0, l1, l2;
-                const bool ok = inside && contributor < last_contributor &&
-                                eval_pair(a, b, c, pfx, pfy, pg, k0, k1, k2, l0, l1, l2);
-                if (!__any_sync(0xffffffffu, ok)) continue;
-                float g[GA_GRAD_F];
-#pragma unroll
-                for (int f = 0; f < GA_GRAD_F; f++) g[f] = 0.f;
-                if (ok) {
-                    const float4 nr = s_rec[3][jj], gb = s_rec[5][jj];
-                    const float alpha = pg.alpha, G = pg.G, c_d = pg.depth, opa = c.w;
-                    const float inv1ma = fast_rcp(1.f - alpha);
-                    T = T * inv1ma;
-                    const float w = alpha * T;
-                    float dL_dalpha = 0.0f;
-                    ar0 = last_alpha * lc0 + (1.f - last_alpha) * ar0; lc0 = nr.w;
-                    ar1 = last_alpha * lc1 + (1.f - last_alpha) * ar1; lc1 = gb.x;
-                    ar2 = last_alpha * lc2 + (1.f - last_alpha) * ar2; lc2 = gb.y;
-                    dL_dalpha += (nr.w - ar0) * dpx0 + (gb.x - ar1) * dpx1 + (gb.y - ar2) * dpx2;
-                    g[15] = w * dpx0; g[16] = w * dpx1; g[17] = w * dpx2;
-                    float dL_dz = 0.0f;
-                    const float inv_cd = fast_rcp(c_d);
-                    const float m_d = GA_M_C0 - GA_M_C1 * inv_cd;
-                    const float dmd_dd = GA_M_C1 * inv_cd * inv_cd;
-                    if (contributor == median_contributor - 1) dL_dz += dL_dmedian;
-                    const float dL_dweight = (final_D2 + m_d * m_d * final_A - 2 * m_d * final_D) * dL_dreg;
-                    dL_dalpha += dL_dweight - last_dL_dT;
-                    last_dL_dT = dL_dweight * alpha + (1 - alpha) * last_dL_dT;
-                    const float dL_dmd = 2.0f * (T * alpha) * (m_d * final_A - final_D) * dL_dreg;
-                    dL_dz += dL_dmd * dmd_dd;
-                    accum_depth_rec = last_alpha * last_depth + (1.f - last_alpha) * accum_depth_rec;
-                    last_depth = c_d;
-                    dL_dalpha += (c_d - accum_depth_rec) * dL_ddepth;
-                    accum_alpha_rec = last_alpha + (1.f - last_alpha) * accum_alpha_rec;
-                    dL_dalpha += (1 - accum_alpha_rec) * dL_daccum;
-                    an0 = last_alpha * ln0 + (1.f - last_alpha) * an0; ln0 = nr.x;
-                    an1 = last_alpha * ln1 + (1.f - last_alpha) * an1; ln1 = nr.y;
-                    an2 = last_alpha * ln2 + (1.f - last_alpha) * an2; ln2 = nr.z;
-                    dL_dalpha += (nr.x - an0) * dn0 + (nr.y - an1) * dn1 + (nr.z - an2) * dn2;
-                    g[11] = w * dn0; g[12] = w * dn1; g[13] = w * dn2;
-                    dL_dalpha *= T;
-                    last_alpha = alpha;
-                    dL_dalpha += (-T_final * inv1ma) * bg_dot_dpixel;
-                    const float dL_dG = opa * dL_dalpha;       // clamp passed through (upstream)
-                    dL_dz += w * dL_ddepth;
-                    if (pg.use3d) {
-                        const float Tw0 = b.z, Tw1 = b.w;
-                        const float dL_ds0 = dL_dG * -G * pg.s0 + dL_dz * Tw0;
-                        const float dL_ds1 = dL_dG * -G * pg.s1 + dL_dz * Tw1;
-                        const float ip = fast_rcp(pg.p2);
-                        const float q0 = dL_ds0 * ip, q1 = dL_ds1 * ip;
-                        const float q2 = -(q0 * pg.s0 + q1 * pg.s1);
-                        const float dk0 = l1 * q2 - l2 * q1, dk1 = l2 * q0 - l0 * q2, dk2 = l0 * q1 - l1 * q0;
-                        const float dl0 = q1 * k2 - q2 * k1, dl1 = q2 * k0 - q0 * k2, dl2 = q0 * k1 - q1 * k0;
-                        g[0] = -dk0; g[1] = -dk1; g[2] = -dk2;
-                        g[3] = -dl0; g[4] = -dl1; g[5] = -dl2;
-                        g[6] = pfx * dk0 + pfy * dl0 + dL_dz * pg.s0;
-                        g[7] = pfx * dk1 + pfy * dl1 + dL_dz * pg.s1;
-                        g[8] = pfx * dk2 + pfy * dl2 + dL_dz;
-                    } else {
-                        g[9] = dL_dG * (-G * GA_FILTER_INV_SQUARE * pg.dx);
-                        g[10] = dL_dG * (-G * GA_FILTER_INV_SQUARE * pg.dy);
-                        g[8] = dL_dz;
-                    }
-                    g[14] = G * dL_dalpha;
-                }
-                // recursive-halving reduction of the 18 components over 32 lanes in
-                // 9+5+3+2+1 = 20 exchanges (a butterfly per component would take 90):
-                // each level halves the component set a lane is responsible for.
-                {
-                    const bool u4 = lane & 16, u3 = lane & 8, u2 = lane & 4, u1 = lane & 2, u0 = lane & 1;
-                    float a9[10];
-#pragma unroll
-                    for (int i = 0; i < 9; i++) {
-                        const float keep = u4 ? g[9 + i] : g[i], send = u4 ? g[i] : g[9 + i];
-                        a9[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-                    }
-                    a9[9] = 0.f;
-                    float b5[6];
-#pragma unroll
-                    for (int i = 0; i < 5; i++) {
-                        const float keep = u3 ? a9[5 + i] : a9[i], send = u3 ? a9[i] : a9[5 + i];
-                        b5[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-                    }
-                    b5[5] = 0.f;
-                    float c3[4];
-#pragma unroll
-                    for (int i = 0; i < 3; i++) {
-                        const float keep = u2 ? b5[3 + i] : b5[i], send = u2 ? b5[i] : b5[3 + i];
-                        c3[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-                    }
-                    c3[3] = 0.f;
-                    float d2[2];
-#pragma unroll
-                    for (int i = 0; i < 2; i++) {
-                        const float keep = u1 ? c3[2 + i] : c3[i], send = u1 ? c3[i] : c3[2 + i];
-                        d2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-                    }
-                    const float keep = u0 ? d2[1] : d2[0], send = u0 ? d2[0] : d2[1];
-                    const float tot = keep + __shfl_xor_sync(0xffffffffu, send, 1);
-                    const int i4 = (u0 ? 1 : 0) + (u1 ? 2 : 0);          // index inside the 3-group
-                    const int i3 = i4 + (u2 ? 3 : 0);                    // inside the 5-group
-                    const int i2 = i3 + (u3 ? 5 : 0);                    // inside the 9-group
-                    const int comp = i2 + (u4 ? 9 : 0);
-                    if (i4 < 3 && i3 < 5 && i2 < 9) atomicAdd(&s_acc[jj][comp], tot);
-                }
-                if (lane == 0) s_touched[jj] = 1;
-            }
-        }
-        __syncthreads();
-        if ((int)threadIdx.x < cnt && s_touched[threadIdx.x]) {
-            float *dst = acc_base + (size_t)s_id[threadIdx.x] * GA_GRAD_F;
-#pragma unroll
-            for (int f = 0; f < GA_GRAD_F; f++) {
-                const float v = s_acc[threadIdx.x][f];
-                if (v != 0.f) atomicAdd(dst + f, v);
-            }
-        }
-        __syncthreads();
-    }
-}
-
 cudaError_t ga_launch_render_bwd(const RasterDims &d, const RasterWs &w, const float *bg,
                                  const float *dL_dcolor, const float *dL_dallmap,
                                  float *grad_acc, cudaStream_t s)
@@ -914,9 +557,6 @@ cudaError_t ga_launch_render_bwd(const RasterDims &d, const RasterWs &w, const f
         attr_set = true;
     }
     dim3 grid(d.gx, d.gy, d.NV);
-    static int variant = -1;
-    if (variant < 0) { const char *e = getenv("GA_B200_BWD"); variant = (e && e[0] == '2') ? 2 : 3; }   // default: two-phase
-    if (variant == 3) render_bwd_kernel<<<grid, 256, sizeof(BwdSmem), s>>>(d, w, bg, dL_dcolor, dL_dallmap, grad_acc);
-    else render_bwd_kernel_v2<<<grid, 256, 0, s>>>(d, w, bg, dL_dcolor, dL_dallmap, grad_acc);
+    render_bwd_kernel<<<grid, 256, sizeof(BwdSmem), s>>>(d, w, bg, dL_dcolor, dL_dallmap, grad_acc);
     return cudaGetLastError();
 }

@@ -66,3 +66,16 @@ torch.cuda.synchronize()
 ts = [cpu_only() for _ in range(30)]
 torch.cuda.synchronize()
 print("host time to enqueue one step (median):          %.3f ms" % (np.median(ts) * 1e3))
+
+if "profile" in sys.argv:
+    import cProfile
+    import pstats
+    pr = cProfile.Profile()
+    torch.cuda.synchronize()
+    pr.enable()
+    for _ in range(40):
+        step("full", True)
+    torch.cuda.synchronize()
+    pr.disable()
+    st = pstats.Stats(pr)
+    st.sort_stats("cumulative").print_stats(45)
