@@ -348,6 +348,7 @@ def run_gpu(args):
                 dit_leg["tensor_peak_tflops"] = tpk
                 dit_leg["frac_of_bf16_peak_sustained"] = dit_leg["tflops"] / float(pk.get("bf16_tflops_sustained", 1400.0))
                 dit_leg["deployed_L_N768"] = run_dit_deployed_leg(dev)
+                dit_leg["C4_L_N4096"] = run_dit_deployed_leg(dev, nfe=10, N=4096)
             except Exception as ex:                      # the raster metric is the headline; report, do not hide
                 dit_leg = {"error": repr(ex)}
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -460,14 +461,15 @@ def run_dit_leg(dev, steps_grid=50, reps=3):
                         "gemm_mlp1_gelu": {"ms": 1e3 * t_gemm, "tflops": fl_gemm / t_gemm / 1e12}}}
 
 
-def run_dit_deployed_leg(dev, nfe=20):
-    """Deployed sizes: DiT-PixArt-PCD-CLAY-L (stage 1, C=3) and ...-stage2-L (C=10 + xyz PE),
-    L24 D1024 H16, N=768 latent points, M=1369 DINO tokens, CFG batch 2.  Reports ms per NFE of each stage and the
-    DiT part of the cascade at the reference's 250-point grids (2 x 249 NFE) derived from it."""
+def run_dit_deployed_leg(dev, nfe=20, N=768):
+    """DiT-PixArt-PCD-CLAY-L (stage 1, C=3) and ...-stage2-L (C=10 + xyz PE), L24 D1024 H16, M=1369 DINO tokens, CFG
+    batch 2, at N latent points: N=768 is the deployed size, N=4096 is BASELINE configs[3] (C4).
+    Reports ms per NFE of each stage and the DiT part of the cascade at the reference's 250-point grids
+    (2 x 249 NFE) derived from it."""
     import torch
     from gaussiananything_b200 import dit
     torch.manual_seed(0)
-    N, M, Dc, B = 768, 1369, 1024, 2
+    M, Dc, B = 1369, 1024, 2
     out = {}
     for name, cin, stage2 in (("DiT-PixArt-PCD-CLAY-L", 3, False), ("DiT-PixArt-PCD-CLAY-stage2-L", 10, True)):
         m = dit.DiT_models[name](input_size=32, num_classes=0, learn_sigma=False, in_channels=cin, context_dim=Dc,

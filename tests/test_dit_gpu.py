@@ -256,3 +256,30 @@ def test_dit_b_full_size_properties():
     ctx_sw = {k: v.flip(0).contiguous() for k, v in ctx.items()}
     y3 = m(x.flip(0).contiguous(), t.flip(0).contiguous(), ctx_sw)
     assert rel(y3.flip(0), y1) < 1e-5
+
+
+def test_dit_l_c4_size_properties():
+    """BASELINE configs[3] size: DiT-L stage 1 and stage 2 at N=4096, d=1024.  The oracle cannot run this in seconds,
+    so size-independent properties only: finite, run-to-run identical bits, batch items independent."""
+    from gaussiananything_b200 import dit
+    dev = torch.device("cuda:0")
+    torch.manual_seed(1)
+    B, N, M = 2, 4096, 1369
+    for name, cin, stage2 in (("DiT-PixArt-PCD-CLAY-L", 3, False), ("DiT-PixArt-PCD-CLAY-stage2-L", 10, True)):
+        m = dit.DiT_models[name](input_size=32, num_classes=0, learn_sigma=False, in_channels=cin, context_dim=1024,
+                                 roll_out=True, pooling_ctx_dim=768)
+        m.randomize_zero_init_().to(dev)
+        x = torch.randn(B, N, cin, device=dev)
+        t = torch.rand(B, device=dev)
+        ctx = {"img_crossattn": torch.randn(B, M, 1024, device=dev), "img_vector": torch.randn(B, 1024, device=dev)}
+        if stage2:
+            ctx["fps-xyz"] = torch.rand(B, N, 3, device=dev) - 0.5
+        y1 = m(x, t, ctx)
+        y2 = m(x, t, ctx)
+        assert y1.shape == (B, N, cin)
+        assert torch.isfinite(y1).all() and torch.equal(y1, y2) and float(y1.abs().mean()) > 0
+        ctx_sw = {k: v.flip(0).contiguous() for k, v in ctx.items()}
+        y3 = m(x.flip(0).contiguous(), t.flip(0).contiguous(), ctx_sw)
+        assert rel(y3.flip(0), y1) < 1e-5
+        del m
+        torch.cuda.empty_cache()

@@ -10,3 +10,5 @@ import bench  # noqa: E402
 dev = torch.device("cuda:0")
 print(json.dumps(bench.run_dit_leg(dev)))
 print(json.dumps(bench.run_dit_deployed_leg(dev)))
+if "c4" in sys.argv:
+    print(json.dumps(bench.run_dit_deployed_leg(dev, nfe=10, N=4096)))
