@@ -213,8 +213,8 @@ cudaError_t ga_launch_render_fwd(const RasterDims &d, const RasterWs &w, const f
 // ---------------------------------------------------------------------------
 // K4 backward
 //
-// Two phases per group of G staged surfels (G = 32, 16 or 8, picked per chunk so that a surfel's cull box
-// clipped to the tile never holds more pixels than its list capacity 2048/G):
+// Two phases per group of G staged surfels (G = 128, 64, 32 or 16, picked per chunk so that a surfel's cull box
+// clipped to the tile never holds more pixels than its list capacity BWD_LIST_RECORDS/G):
 //   phase A (pixel-parallel, back to front): every lane walks its own stream of surfels whose cull box
 //     contains its pixel, recomputes alpha, runs the compositing recurrences and appends a 16-byte record
 //     (pixel, dL/dalpha, dL/dz, w) to the surfel's list in shared memory;
@@ -366,6 +366,8 @@ __device__ __forceinline__ void bwd_phase_b(BwdSmem &sm, const int *cnt, int g0,
     }
 }
 
+// Two CTAs per SM (96 KB of shared memory, 128 registers).  Three per SM (2560-record lists, 80 registers) were
+// measured at 0.85 ms against 0.55 ms: the phase-A recurrences do not fit 80 registers (192 B of spills).
 __global__ void __launch_bounds__(256, 2)
 render_bwd_kernel(RasterDims d, RasterWs ws, const float *__restrict__ bg,
                   const float *__restrict__ dL_dcolor, const float *__restrict__ dL_dallmap,
