@@ -62,7 +62,7 @@ extern "C" int ga_raster_layout(int batch, int P, int views, int H, int W,
     L->rec = off;        off = align_up(off + NVP * GA_REC_F * sizeof(float), 256);
     L->depth = off;      off = align_up(off + NVP * sizeof(float), 256);
     L->rect = off;       off = align_up(off + NVP * sizeof(uint32_t), 256);
-    L->tile_count = off; off = align_up(off + NVT * sizeof(uint32_t), 256);
+    L->tile_count = off; off = align_up(off + NVT * GA_TILE_REPLICAS * sizeof(uint32_t), 256);
     L->tile_start = off; off = align_up(off + (NVT + 1) * sizeof(uint32_t), 256);
     L->keys = off;       off = align_up(off + mi * sizeof(uint64_t), 256);
     L->ids = off;        off = align_up(off + mi * sizeof(uint32_t), 256);
@@ -108,7 +108,7 @@ static int raster_forward_impl(int stage, const float *gauss13, int batch, int P
     cudaError_t e;
     if (stage == 0 || stage == 1) {
         if ((e = cudaMemsetAsync(w.status, 0, 16 * sizeof(int32_t), s)) != cudaSuccess) return (int)e;
-        if ((e = cudaMemsetAsync(w.tile_count, 0, (size_t)d.NV * d.T * sizeof(uint32_t), s)) != cudaSuccess) return (int)e;
+        if ((e = cudaMemsetAsync(w.tile_count, 0, (size_t)d.NV * d.T * GA_TILE_REPLICAS * sizeof(uint32_t), s)) != cudaSuccess) return (int)e;
         prof(0, s);
         if ((e = ga_launch_preprocess(d, w, gauss13, viewmats, projmats, out_radii, s)) != cudaSuccess) return (int)e;
         prof(1, s);

@@ -25,7 +25,18 @@ scan_tiles_kernel(RasterDims d, RasterWs ws)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int base = 0; base < n; base += SCAN_THREADS) {
         const int i = base + threadIdx.x;
-        uint32_t v = (i < n) ? ws.tile_count[i] : 0u;
+        uint32_t rep[GA_TILE_REPLICAS];
+        uint32_t v = 0u;
+        if (i < n) {
+            const uint4 *src = reinterpret_cast<const uint4 *>(ws.tile_count + (size_t)i * GA_TILE_REPLICAS);
+#pragma unroll
+            for (int q = 0; q < GA_TILE_REPLICAS / 4; q++) {
+                const uint4 c = src[q];
+                rep[4 * q] = c.x; rep[4 * q + 1] = c.y; rep[4 * q + 2] = c.z; rep[4 * q + 3] = c.w;
+            }
+#pragma unroll
+            for (int q = 0; q < GA_TILE_REPLICAS; q++) v += rep[q];
+        }
         uint32_t x = v;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -48,7 +59,15 @@ scan_tiles_kernel(RasterDims d, RasterWs ws)
         const uint32_t excl = carry + s_warp[warp] + x - v;
         if (i < n) {
             ws.tile_start[i] = excl;
-            ws.tile_count[i] = 0;       // becomes the scatter fill cursor
+            // every replica becomes the absolute fill cursor of its own sub-range of the tile's slots
+            uint32_t run = excl;
+            uint32_t cur[GA_TILE_REPLICAS];
+#pragma unroll
+            for (int q = 0; q < GA_TILE_REPLICAS; q++) { cur[q] = run; run += rep[q]; }
+            uint4 *dst = reinterpret_cast<uint4 *>(ws.tile_count + (size_t)i * GA_TILE_REPLICAS);
+#pragma unroll
+            for (int q = 0; q < GA_TILE_REPLICAS / 4; q++)
+                dst[q] = make_uint4(cur[4 * q], cur[4 * q + 1], cur[4 * q + 2], cur[4 * q + 3]);
         }
         __syncthreads();
         if (threadIdx.x == SCAN_THREADS - 1) s_carry = excl + v;
@@ -74,11 +93,14 @@ scatter_kernel(RasterDims d, RasterWs ws)
     const int x0 = r & 255, y0 = (r >> 8) & 255, x1 = (r >> 16) & 255, y1 = r >> 24;
     const unsigned long long key =
         ((unsigned long long)__float_as_uint(ws.depth[vi]) << 32) | (unsigned long long)(uint32_t)i;
+    // same replica as in K1 (same launch geometry: 256 threads, surfel i -> thread i % 256), so every replica
+    // receives exactly the instances it counted
+    const int rep = (threadIdx.x >> 5) & (GA_TILE_REPLICAS - 1);
     for (int y = y0; y < y1; y++)
         for (int x = x0; x < x1; x++) {
             const size_t t = (size_t)view * d.T + y * d.gx + x;
-            const uint32_t slot = atomicAdd(&ws.tile_count[t], 1u);
-            ws.keys[ws.tile_start[t] + slot] = key;
+            const uint32_t slot = atomicAdd(&ws.tile_count[t * GA_TILE_REPLICAS + rep], 1u);
+            ws.keys[slot] = key;
         }
 }
 

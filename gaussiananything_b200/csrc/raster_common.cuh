@@ -48,6 +48,12 @@ cudaError_t ga_launch_preprocess(const RasterDims &d, const RasterWs &w, const f
 // status_host / status_event (both optional): after the tile scan -- the first point where the instance count and
 // the overflow flag are known -- status[0..3] is copied to pinned host memory and the event recorded, so the host
 // can look at them while the scatter / sort / composite kernels are still running.
+// Tile counters / scatter cursors are kept in GA_TILE_REPLICAS copies per tile (replica = warp index mod R): the
+// 1.05M atomics of the C2 scene otherwise queue up on 6144 addresses, ~170 deep, and L2 serialises same-address
+// atomics (scatter: 48 us for 1M atomics).  The scan sums the replicas of a tile and hands every replica its own
+// sub-range of the tile's slots; the order inside a tile is fixed afterwards by the sort, so results do not change.
+#define GA_TILE_REPLICAS 8
+
 cudaError_t ga_launch_binning(const RasterDims &d, const RasterWs &w, cudaStream_t s, int32_t *status_host = nullptr,
                               cudaEvent_t status_event = nullptr);
 cudaError_t ga_launch_render_fwd(const RasterDims &d, const RasterWs &w, const float *bg,

@@ -163,9 +163,9 @@ preprocess_kernel(RasterDims d, RasterWs ws, const float *__restrict__ gauss13,
     if (radius_i > 0) {
         const int x0 = rect_packed & 255, y0 = (rect_packed >> 8) & 255;
         const int x1 = (rect_packed >> 16) & 255, y1 = rect_packed >> 24;
-        uint32_t *tc = ws.tile_count + (size_t)view * d.T;
+        uint32_t *tc = ws.tile_count + (size_t)view * d.T * GA_TILE_REPLICAS + ((threadIdx.x >> 5) & (GA_TILE_REPLICAS - 1));
         for (int y = y0; y < y1; y++)
-            for (int x = x0; x < x1; x++) atomicAdd(&tc[y * d.gx + x], 1u);
+            for (int x = x0; x < x1; x++) atomicAdd(&tc[(y * d.gx + x) * GA_TILE_REPLICAS], 1u);
     }
 }
 
