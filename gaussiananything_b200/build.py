@@ -48,7 +48,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
         if (not force and os.path.exists(obj)
                 and os.path.getmtime(obj) >= max(os.path.getmtime(src), hdr_m)):
             continue
-        cmd = [nvcc] + ARCH + COMMON + EXTRA.get(f, []) + ["-c", src, "-o", obj]
+        # GA_B200_NVCC_EXTRA="-DFOO=1 ...": extra flags for every file (tuning experiments; use with --force)
+        cmd = [nvcc] + ARCH + COMMON + EXTRA.get(f, []) + os.environ.get("GA_B200_NVCC_EXTRA", "").split() + ["-c", src, "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         r = subprocess.run(cmd, capture_output=True, text=True)

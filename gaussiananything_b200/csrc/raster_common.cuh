@@ -52,7 +52,9 @@ cudaError_t ga_launch_preprocess(const RasterDims &d, const RasterWs &w, const f
 // 1.05M atomics of the C2 scene otherwise queue up on 6144 addresses, ~170 deep, and L2 serialises same-address
 // atomics (scatter: 48 us for 1M atomics).  The scan sums the replicas of a tile and hands every replica its own
 // sub-range of the tile's slots; the order inside a tile is fixed afterwards by the sort, so results do not change.
+#ifndef GA_TILE_REPLICAS
 #define GA_TILE_REPLICAS 8
+#endif
 
 cudaError_t ga_launch_binning(const RasterDims &d, const RasterWs &w, cudaStream_t s, int32_t *status_host = nullptr,
                               cudaEvent_t status_event = nullptr);
