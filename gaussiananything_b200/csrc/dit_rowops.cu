@@ -161,6 +161,45 @@ layernorm_rows_kernel(const float *__restrict__ x, const float *__restrict__ w, 
     const int lane = threadIdx.x & 31;
     if (r >= R) return;
     const float *xr = x + (size_t)r * D;
+    if ((D & 3) == 0 && D <= 1024) {
+        // row in registers: one round of independent 16-byte loads instead of three dependent passes
+        const float4 *x4 = reinterpret_cast<const float4 *>(xr);
+        const int n4 = D >> 2;
+        float4 cache[8];
+        float s = 0.f;
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            const int i = lane + 32 * u;
+            cache[u] = i < n4 ? x4[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+            s += cache[u].x + cache[u].y + cache[u].z + cache[u].w;
+        }
+        const float mean = warp_sum(s) / (float)D;
+        float v = 0.f;
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            if (lane + 32 * u < n4) {
+                const float d0 = cache[u].x - mean, d1 = cache[u].y - mean, d2 = cache[u].z - mean, d3 = cache[u].w - mean;
+                v += d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
+            }
+        }
+        const float rs = rsqrtf(warp_sum(v) / (float)D + eps);
+        float4 *y4 = reinterpret_cast<float4 *>(y + (size_t)r * D);
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            const int i = lane + 32 * u;
+            if (i < n4) {
+                float4 o = make_float4((cache[u].x - mean) * rs, (cache[u].y - mean) * rs, (cache[u].z - mean) * rs,
+                                       (cache[u].w - mean) * rs);
+                if (w) {
+                    const float4 ww = __ldg(reinterpret_cast<const float4 *>(w) + i);
+                    const float4 bb = bvec ? __ldg(reinterpret_cast<const float4 *>(bvec) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    o.x = o.x * ww.x + bb.x; o.y = o.y * ww.y + bb.y; o.z = o.z * ww.z + bb.z; o.w = o.w * ww.w + bb.w;
+                }
+                y4[i] = o;
+            }
+        }
+        return;
+    }
     float s = 0.f;
     for (int i = lane; i < D; i += 32) s += xr[i];
     const float mean = warp_sum(s) / (float)D;
