@@ -53,8 +53,10 @@ _status_slots = {}
 
 
 def _status_slot(dev):
-    """Per-device pinned 4-int buffer + event for the overlapped status read-back of ga_raster_forward_async."""
-    key = (dev.type, dev.index if dev.index is not None else torch.cuda.current_device())
+    """Pinned 4-int buffer + event for the overlapped status read-back of ga_raster_forward_async."""
+    # one slot per (device, stream): calls on different streams may overlap on the host
+    key = (dev.index if dev.index is not None else torch.cuda.current_device(),
+           torch.cuda.current_stream(dev).cuda_stream)
     slot = _status_slots.get(key)
     if slot is None:
         ev = torch.cuda.Event()
