@@ -42,3 +42,20 @@ def test_cascade_shapes_and_surfel_invariants():
     parent = out["gaussians_upsampled"][..., :3].reshape(B, N, 8, 3)
     child = out["gaussians_upsampled_2"][..., :3].reshape(B, N, 8, 4, 3)
     assert float((child - parent[:, :, :, None]).abs().max()) <= 0.5 * g["scene_max"] + 1e-6
+
+
+def test_decoded_surfels_render_through_the_surfel_oracle():
+    """Row N1's output is row a1's input: the [B, N*f, 13] buffer the decoder produces goes straight into the
+    rasteriser (here the CPU oracle, one 64 x 64 view) -- finite image, part of it covered."""
+    import numpy as np
+    from oracle import surfel_oracle as so
+    g = vo.load_golden(GOLD)
+    with torch.no_grad():
+        out = vo.decode(g["sd"], g["latent"], g["xyz"], g["heads"], g["depth"], g["scene_max"], g["skip_weight"])
+    s = out["gaussians_upsampled_3"][0].numpy().astype(np.float32)          # [6144, 13]
+    view, proj, _pos, _tan = so.camera_from_pose25(so.orbit_pose25(30.0, 20.0))
+    r = so.rasterize(s[:, 0:3], s[:, 3:4], s[:, 4:6], s[:, 6:10], s[:, 10:13], view, proj,
+                     np.zeros(3, np.float32), 64, 64)
+    assert np.isfinite(r["color"]).all() and np.isfinite(r["allmap"]).all()
+    alpha = r["allmap"][1]
+    assert float(alpha.max()) > 0.05 and int((r["radii"] > 0).sum()) > 100
