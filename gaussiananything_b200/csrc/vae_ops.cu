@@ -1,0 +1,348 @@
+// Row-wise kernels of the VAE decode path latent tokens -> surfels: everything
+// around the tcgen05 GEMMs / attention that the DiT kernels do not already cover.
+//   layernorm_modulate : LayerNorm [* w + b] [* (1 + scale[row]) + shift[row]] -> bf16      (DiTBlock2, PreNorm)
+//   thin_linear        : [LayerNorm affine] [SiLU] x . W^T + b with <= 16 outputs              (conv_sr, residual heads)
+//   micro_attention    : qk-normed attention over sequences of <= 16 tokens, one warp per (sequence, head)
+//   micro_seq_build    : [parent token ; f learned queries] sequences of the cascaded up-samplers
+//   surfel_cascade_pack: residual + parent pre-activation -> activations -> packed [R, 13] surfels
+// Math follows /root/reference/vit/vit_triplane.py:287-345,991-1064,1289-1313,1388-1440,
+// /root/reference/dit/dit_decoder.py:15-42, /root/reference/nsr/srt/layers.py:82-90,146-186 and
+// /root/reference/vit/vision_transformer.py:215-303; the checker is oracle/vae_decoder_oracle.py.
+#include "../../include/ga_b200.h"
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+namespace {
+
+__device__ __forceinline__ float wsum(float v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+
+// one warp per row, row cached in registers (D % 4 == 0, D <= 1024)
+__global__ void __launch_bounds__(256)
+layernorm_modulate_kernel(const float *__restrict__ x, const float *__restrict__ w, const float *__restrict__ bias,
+                          const float *__restrict__ shift, const float *__restrict__ scale, int mod_ld,
+                          int rows_per_batch, __nv_bfloat16 *__restrict__ out, int R, int D, float eps)
+{
+    const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (r >= R) return;
+    const float4 *x4 = reinterpret_cast<const float4 *>(x + (size_t)r * D);
+    const int n4 = D >> 2;
+    float4 c[8];
+    float s = 0.f;
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+        const int i = lane + 32 * u;
+        c[u] = i < n4 ? x4[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+        s += (c[u].x + c[u].y) + (c[u].z + c[u].w);
+    }
+    const float mean = wsum(s) / (float)D;
+    float v = 0.f;
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+        if (lane + 32 * u < n4) {
+            const float d0 = c[u].x - mean, d1 = c[u].y - mean, d2 = c[u].z - mean, d3 = c[u].w - mean;
+            v += d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
+        }
+    }
+    const float rs = rsqrtf(wsum(v) / (float)D + eps);
+    const int b = r / rows_per_batch;
+    const float4 *w4 = reinterpret_cast<const float4 *>(w), *b4 = reinterpret_cast<const float4 *>(bias);
+    const float4 *sh4 = shift ? reinterpret_cast<const float4 *>(shift + (size_t)b * mod_ld) : nullptr;
+    const float4 *sc4 = scale ? reinterpret_cast<const float4 *>(scale + (size_t)b * mod_ld) : nullptr;
+    uint2 *o = reinterpret_cast<uint2 *>(out + (size_t)r * D);
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+        const int i = lane + 32 * u;
+        if (i < n4) {
+            float4 y = make_float4((c[u].x - mean) * rs, (c[u].y - mean) * rs, (c[u].z - mean) * rs, (c[u].w - mean) * rs);
+            if (w) {
+                const float4 ww = __ldg(w4 + i);
+                y.x *= ww.x; y.y *= ww.y; y.z *= ww.z; y.w *= ww.w;
+            }
+            if (bias) {
+                const float4 bb = __ldg(b4 + i);
+                y.x += bb.x; y.y += bb.y; y.z += bb.z; y.w += bb.w;
+            }
+            if (sc4) {
+                const float4 a = __ldg(sc4 + i), t = __ldg(sh4 + i);
+                y.x = y.x * (1.f + a.x) + t.x; y.y = y.y * (1.f + a.y) + t.y;
+                y.z = y.z * (1.f + a.z) + t.z; y.w = y.w * (1.f + a.w) + t.w;
+            }
+            __nv_bfloat162 p0 = __floats2bfloat162_rn(y.x, y.y), p1 = __floats2bfloat162_rn(y.z, y.w);
+            o[i] = make_uint2(*reinterpret_cast<uint32_t *>(&p0), *reinterpret_cast<uint32_t *>(&p1));
+        }
+    }
+}
+
+// y[r, c] = b[c] + sum_d f(x[r])[d] W[c, d], f = [LayerNorm affine] then [SiLU]; one warp per row; C <= 16
+__global__ void __launch_bounds__(256)
+thin_linear_kernel(const float *__restrict__ x, const float *__restrict__ ln_w, const float *__restrict__ ln_b,
+                   int apply_silu, const float *__restrict__ W, const float *__restrict__ bias,
+                   float *__restrict__ y, int R, int D, int C, float eps)
+{
+    const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (r >= R) return;
+    const float4 *x4 = reinterpret_cast<const float4 *>(x + (size_t)r * D);
+    const int n4 = D >> 2;
+    float4 c[8];
+    float s = 0.f;
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+        const int i = lane + 32 * u;
+        c[u] = i < n4 ? x4[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+        s += (c[u].x + c[u].y) + (c[u].z + c[u].w);
+    }
+    float mean = 0.f, rs = 1.f;
+    if (ln_w) {
+        mean = wsum(s) / (float)D;
+        float v = 0.f;
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            if (lane + 32 * u < n4) {
+                const float d0 = c[u].x - mean, d1 = c[u].y - mean, d2 = c[u].z - mean, d3 = c[u].w - mean;
+                v += d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
+            }
+        }
+        rs = rsqrtf(wsum(v) / (float)D + eps);
+    }
+    float acc[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) acc[k] = 0.f;
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+        const int i = lane + 32 * u;
+        if (i < n4) {
+            float4 h = c[u];
+            if (ln_w) {
+                const float4 ww = __ldg(reinterpret_cast<const float4 *>(ln_w) + i);
+                const float4 bb = ln_b ? __ldg(reinterpret_cast<const float4 *>(ln_b) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+                h.x = (h.x - mean) * rs * ww.x + bb.x; h.y = (h.y - mean) * rs * ww.y + bb.y;
+                h.z = (h.z - mean) * rs * ww.z + bb.z; h.w = (h.w - mean) * rs * ww.w + bb.w;
+            }
+            if (apply_silu) { h.x = silu_f(h.x); h.y = silu_f(h.y); h.z = silu_f(h.z); h.w = silu_f(h.w); }
+#pragma unroll
+            for (int k = 0; k < 16; k++) {
+                if (k < C) {
+                    const float4 wk = __ldg(reinterpret_cast<const float4 *>(W + (size_t)k * D) + i);
+                    acc[k] += h.x * wk.x + h.y * wk.y + h.z * wk.z + h.w * wk.w;
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        if (k < C) {
+            const float t = wsum(acc[k]);
+            if (lane == 0) y[(size_t)r * C + k] = t + (bias ? bias[k] : 0.f);
+        }
+    }
+}
+
+// Attention over micro-sequences: qkv bf16 [S*L, 3*H*64] in "(K H D)" column order (q | k | v), per-head RMSNorm of
+// q and k (weights qn_w, kn_w [64]), softmax(q k^T / 8) v, out bf16 [S*L, H*64].  One warp per (sequence, head); the
+// L x 64 tiles live in shared memory as fp32 (rows padded to 65 floats: conflict-free column walks).
+constexpr int kMicroL = 16, kMicroPitch = 65, kMicroWarps = 4;
+constexpr int kMicroSmemPerWarp = (3 * kMicroL * kMicroPitch + kMicroL * (kMicroL + 1)) * (int)sizeof(float);
+
+__global__ void __launch_bounds__(32 * kMicroWarps)
+micro_attention_kernel(const __nv_bfloat16 *__restrict__ qkv, const float *__restrict__ qn_w,
+                       const float *__restrict__ kn_w, __nv_bfloat16 *__restrict__ out, int S, int L, int H, float eps)
+{
+    extern __shared__ float micro_smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long item = (long long)blockIdx.x * kMicroWarps + warp;
+    if (item >= (long long)S * H) return;
+    const int s = (int)(item / H), h = (int)(item % H);
+    float *sq = micro_smem + (size_t)warp * (kMicroSmemPerWarp / sizeof(float));
+    float *sk = sq + kMicroL * kMicroPitch, *sv = sk + kMicroL * kMicroPitch, *sp = sv + kMicroL * kMicroPitch;
+    const int C = H * 64;
+    const float wq0 = qn_w[2 * lane], wq1 = qn_w[2 * lane + 1], wk0 = kn_w[2 * lane], wk1 = kn_w[2 * lane + 1];
+    for (int i = 0; i < L; i++) {
+        const __nv_bfloat16 *row = qkv + ((size_t)s * L + i) * (3 * C) + h * 64 + 2 * lane;
+        const float2 q = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(row));
+        const float2 k = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(row + C));
+        const float2 v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(row + 2 * C));
+        const float rq = rsqrtf(wsum(q.x * q.x + q.y * q.y) * (1.0f / 64.0f) + eps);
+        const float rk = rsqrtf(wsum(k.x * k.x + k.y * k.y) * (1.0f / 64.0f) + eps);
+        sq[i * kMicroPitch + 2 * lane] = q.x * rq * wq0; sq[i * kMicroPitch + 2 * lane + 1] = q.y * rq * wq1;
+        sk[i * kMicroPitch + 2 * lane] = k.x * rk * wk0; sk[i * kMicroPitch + 2 * lane + 1] = k.y * rk * wk1;
+        sv[i * kMicroPitch + 2 * lane] = v.x; sv[i * kMicroPitch + 2 * lane + 1] = v.y;
+    }
+    __syncwarp();
+    for (int e = lane; e < L * L; e += 32) {                  // scores, scaled by 1/sqrt(64)
+        const int i = e / L, j = e % L;
+        float a = 0.f;
+#pragma unroll 16
+        for (int d = 0; d < 64; d++) a += sq[i * kMicroPitch + d] * sk[j * kMicroPitch + d];
+        sp[i * (kMicroL + 1) + j] = a * 0.125f;
+    }
+    __syncwarp();
+    if (lane < L) {                                           // one lane per query row
+        float m = -INFINITY;
+        for (int j = 0; j < L; j++) m = fmaxf(m, sp[lane * (kMicroL + 1) + j]);
+        float l = 0.f;
+        for (int j = 0; j < L; j++) {
+            const float p = __expf(sp[lane * (kMicroL + 1) + j] - m);
+            sp[lane * (kMicroL + 1) + j] = p;
+            l += p;
+        }
+        const float inv = 1.0f / l;
+        for (int j = 0; j < L; j++) sp[lane * (kMicroL + 1) + j] *= inv;
+    }
+    __syncwarp();
+    for (int i = 0; i < L; i++) {
+        float o0 = 0.f, o1 = 0.f;
+        for (int j = 0; j < L; j++) {
+            const float p = sp[i * (kMicroL + 1) + j];
+            o0 += p * sv[j * kMicroPitch + 2 * lane];
+            o1 += p * sv[j * kMicroPitch + 2 * lane + 1];
+        }
+        *reinterpret_cast<__nv_bfloat162 *>(out + ((size_t)s * L + i) * C + h * 64 + 2 * lane) = __floats2bfloat162_rn(o0, o1);
+    }
+}
+
+// seq[s, 0, :] = parent token of sequence s, seq[s, 1 + j, :] = queries[j, :]   (fp32 residual stream)
+// parent token: prev_f == 0 -> parents[s, :]; else the j-th child of the previous stage's sequence buffer
+// [S / prev_f, 1 + prev_f, D]:  parents[(s / prev_f) * (1 + prev_f) + 1 + s % prev_f, :]
+__global__ void micro_seq_build_kernel(const float *__restrict__ parents, int prev_f, const float *__restrict__ queries,
+                                       float *__restrict__ seq, long long S, int f, int D)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int n4 = D >> 2;
+    const long long total = S * (1 + f) * n4;
+    if (i >= total) return;
+    const int d4 = (int)(i % n4);
+    const long long row = i / n4;
+    const long long s = row / (1 + f);
+    const int t = (int)(row % (1 + f));
+    float4 v;
+    if (t == 0) {
+        const long long prow = prev_f == 0 ? s : (s / prev_f) * (1 + prev_f) + 1 + (s % prev_f);
+        v = reinterpret_cast<const float4 *>(parents + prow * D)[d4];
+    } else {
+        v = __ldg(reinterpret_cast<const float4 *>(queries + (size_t)(t - 1) * D) + d4);
+    }
+    reinterpret_cast<float4 *>(seq)[i] = v;
+}
+
+// res [R, 13]: raw 13-channel prediction of child r (for the base level: of token r).
+// pre = res + parent_pre[r / f] (parent_pre may be NULL: base level); position = tanh(res[0:3]) * offset_scale +
+// parent_pos[r / f]; channels 3.. from pre: sigmoid | softplus * scale_factor (2) | normalise (4) | 0.5 tanh + 0.5 (3).
+__global__ void surfel_cascade_pack_kernel(const float *__restrict__ res, const float *__restrict__ parent_pre,
+                                           const float *__restrict__ parent_pos, int parent_pos_stride, int f,
+                                           float offset_scale, float scale_factor, float *__restrict__ out_gauss,
+                                           float *__restrict__ out_pre, long long R)
+{
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= R) return;
+    const long long pr = r / f;
+    float p[13];
+#pragma unroll
+    for (int k = 0; k < 13; k++) p[k] = res[r * 13 + k];
+    float g[13];
+#pragma unroll
+    for (int k = 0; k < 3; k++) g[k] = tanhf(p[k]) * offset_scale + parent_pos[pr * parent_pos_stride + k];
+    if (parent_pre) {
+#pragma unroll
+        for (int k = 0; k < 13; k++) p[k] += parent_pre[pr * 13 + k];
+    }
+    g[3] = 1.0f / (1.0f + expf(-p[3]));
+#pragma unroll
+    for (int k = 4; k < 6; k++) g[k] = (p[k] > 20.f ? p[k] : log1pf(expf(p[k]))) * scale_factor;      // F.softplus
+    const float n = fmaxf(sqrtf(p[6] * p[6] + p[7] * p[7] + p[8] * p[8] + p[9] * p[9]), 1e-12f);        // F.normalize
+#pragma unroll
+    for (int k = 6; k < 10; k++) g[k] = p[k] / n;
+#pragma unroll
+    for (int k = 10; k < 13; k++) g[k] = 0.5f * tanhf(p[k]) + 0.5f;
+#pragma unroll
+    for (int k = 0; k < 13; k++) out_gauss[r * 13 + k] = g[k];
+    if (out_pre) {
+#pragma unroll
+        for (int k = 0; k < 13; k++) out_pre[r * 13 + k] = p[k];
+    }
+}
+
+__global__ void silu_to_bf16_kernel(const float *__restrict__ x, __nv_bfloat16 *__restrict__ y, size_t n)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) y[i] = __float2bfloat16(silu_f(x[i]));
+}
+
+inline int last_err() { return (int)cudaGetLastError(); }
+inline bool row_ok(int D) { return D > 0 && (D & 3) == 0 && D <= 1024; }
+
+}  // namespace
+
+extern "C" int ga_layernorm_modulate(const float *x, const float *w, const float *bias, const float *shift,
+                                     const float *scale, int mod_ld, int rows_per_batch, void *out_bf16, int R, int D,
+                                     float eps, void *stream)
+{
+    if (!x || !out_bf16 || R <= 0 || !row_ok(D) || (bias && !w) || ((shift == nullptr) != (scale == nullptr))) return GA_ERR_BADARG;
+    if (shift && (rows_per_batch <= 0 || (mod_ld & 3))) return GA_ERR_BADARG;
+    layernorm_modulate_kernel<<<(R + 7) / 8, 256, 0, (cudaStream_t)stream>>>(
+        x, w, bias, shift, scale, mod_ld, rows_per_batch > 0 ? rows_per_batch : 1, reinterpret_cast<__nv_bfloat16 *>(out_bf16), R,
+        D, eps);
+    return last_err();
+}
+
+extern "C" int ga_thin_linear(const float *x, const float *ln_w, const float *ln_b, int apply_silu, const float *W,
+                              const float *bias, float *y, int R, int D, int C, float eps, void *stream)
+{
+    if (!x || !W || !y || R <= 0 || !row_ok(D) || C <= 0 || C > 16 || (ln_b && !ln_w)) return GA_ERR_BADARG;
+    thin_linear_kernel<<<(R + 7) / 8, 256, 0, (cudaStream_t)stream>>>(x, ln_w, ln_b, apply_silu, W, bias, y, R, D, C, eps);
+    return last_err();
+}
+
+extern "C" int ga_micro_attention_bf16(const void *qkv, const float *qn_w, const float *kn_w, void *out, int S, int L,
+                                       int H, float eps, void *stream)
+{
+    if (!qkv || !qn_w || !kn_w || !out || S <= 0 || L <= 0 || L > kMicroL || H <= 0) return GA_ERR_BADARG;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(micro_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             kMicroWarps * kMicroSmemPerWarp);
+        if (e != cudaSuccess) return (int)e;
+        attr_set = true;
+    }
+    const long long items = (long long)S * H;
+    micro_attention_kernel<<<(unsigned)((items + kMicroWarps - 1) / kMicroWarps), 32 * kMicroWarps,
+                             kMicroWarps * kMicroSmemPerWarp, (cudaStream_t)stream>>>(
+        reinterpret_cast<const __nv_bfloat16 *>(qkv), qn_w, kn_w, reinterpret_cast<__nv_bfloat16 *>(out), S, L, H, eps);
+    return last_err();
+}
+
+extern "C" int ga_micro_seq_build(const float *parents, int prev_f, const float *queries, float *seq, int64_t S, int f,
+                                  int D, void *stream)
+{
+    if (!parents || !queries || !seq || S <= 0 || f <= 0 || prev_f < 0 || !row_ok(D)) return GA_ERR_BADARG;
+    if (prev_f > 0 && S % prev_f) return GA_ERR_BADARG;
+    const long long total = S * (1 + f) * (D >> 2);
+    micro_seq_build_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(parents, prev_f, queries, seq, S,
+                                                                                            f, D);
+    return last_err();
+}
+
+extern "C" int ga_surfel_cascade_pack(const float *res, const float *parent_pre, const float *parent_pos,
+                                      int parent_pos_stride, int f, float offset_scale, float scale_factor,
+                                      float *out_gauss13, float *out_pre, int64_t R, void *stream)
+{
+    if (!res || !parent_pos || !out_gauss13 || R <= 0 || f <= 0 || parent_pos_stride < 3) return GA_ERR_BADARG;
+    surfel_cascade_pack_kernel<<<(unsigned)((R + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        res, parent_pre, parent_pos, parent_pos_stride, f, offset_scale, scale_factor, out_gauss13, out_pre, R);
+    return last_err();
+}
+
+extern "C" int ga_silu_to_bf16(const float *x, void *y, int64_t n, void *stream)
+{
+    if (!x || !y || n <= 0) return GA_ERR_BADARG;
+    silu_to_bf16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        x, reinterpret_cast<__nv_bfloat16 *>(y), (size_t)n);
+    return last_err();
+}

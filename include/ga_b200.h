@@ -211,6 +211,32 @@ int ga_cfg_combine(const float *eps, float *out, int64_t half_elems, float cfg_s
 int ga_axpy(float *x, const float *v, float a, int64_t n, void *stream);          /* x += a v */
 int ga_f32_to_bf16(const float *x, void *y, int64_t n, void *stream);
 
+/* ---- VAE decode path latent tokens -> surfels (building blocks) -------------
+ * Replaces the elementwise / small-matrix torch ops of /root/reference/vit/vit_triplane.py:287-345,991-1064,1289-1313,
+ * 1388-1440, /root/reference/dit/dit_decoder.py:15-42 and /root/reference/nsr/srt/layers.py:82-90,146-186. */
+/* out_bf16[r] = LayerNorm(x[r]) [* w + bias] [* (1 + scale[b]) + shift[b]], b = r / rows_per_batch (1 = per token);
+ * D % 4 == 0, D <= 1024 */
+int ga_layernorm_modulate(const float *x, const float *w, const float *bias, const float *shift, const float *scale,
+                          int mod_ld, int rows_per_batch, void *out_bf16, int R, int D, float eps, void *stream);
+/* y[r, c] = bias[c] + sum_d f(x[r])[d] W[c, d], f = optional LayerNorm (ln_w, ln_b) then optional SiLU; C <= 16 */
+int ga_thin_linear(const float *x, const float *ln_w, const float *ln_b, int apply_silu, const float *W,
+                   const float *bias, float *y, int R, int D, int C, float eps, void *stream);
+/* attention over S sequences of L <= 16 tokens: qkv bf16 [S*L, 3*H*64] ("(K H D)" columns), q/k RMS-normalised per
+ * head with weights qn_w / kn_w [64], softmax(q k^T / 8) v -> out bf16 [S*L, H*64] */
+int ga_micro_attention_bf16(const void *qkv, const float *qn_w, const float *kn_w, void *out, int S, int L, int H,
+                            float eps, void *stream);
+/* seq [S, 1+f, D] fp32: row 0 = the parent token (prev_f == 0: parents[s]; else child s % prev_f of sequence
+ * s / prev_f of the previous stage's [S/prev_f, 1+prev_f, D] buffer), rows 1..f = queries [f, D] */
+int ga_micro_seq_build(const float *parents, int prev_f, const float *queries, float *seq, int64_t S, int f, int D,
+                       void *stream);
+/* child r of parent r / f: pre = res[r] + parent_pre[r/f] (parent_pre NULL at the base level); xyz = tanh(res[r][0:3])
+ * * offset_scale + parent_pos[(r/f) * parent_pos_stride + 0..2]; other channels from pre: sigmoid | softplus *
+ * scale_factor | normalise | 0.5 tanh + 0.5.  out_gauss13 [R,13] is rasteriser input; out_pre [R,13] feeds the next level */
+int ga_surfel_cascade_pack(const float *res, const float *parent_pre, const float *parent_pos, int parent_pos_stride,
+                           int f, float offset_scale, float scale_factor, float *out_gauss13, float *out_pre,
+                           int64_t R, void *stream);
+int ga_silu_to_bf16(const float *x, void *y, int64_t n, void *stream);            /* y = bf16(silu(x)) */
+
 /* Measurement aid: when enabled, cudaEvents are recorded around every kernel
  * stage of the next forward/backward; ga_profile_read synchronises on them and
  * returns per-stage milliseconds: [0] preprocess, [1] binning, [2] render fwd,
