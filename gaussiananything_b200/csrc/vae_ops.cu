@@ -235,7 +235,8 @@ __global__ void micro_seq_build_kernel(const float *__restrict__ parents, int pr
 // res [R, 13]: raw 13-channel prediction of child r (for the base level: of token r).
 // pre = res + parent_pre[r / f] (parent_pre may be NULL: base level); position = tanh(res[0:3]) * offset_scale +
 // parent_pos[r / f]; channels 3.. from pre: sigmoid | softplus * scale_factor (2) | normalise (4) | 0.5 tanh + 0.5 (3).
-__global__ void surfel_cascade_pack_kernel(const float *__restrict__ res, const float *__restrict__ parent_pre,
+__global__ void surfel_cascade_pack_kernel(const float *__restrict__ res, int res_in_sequences,
+                                           const float *__restrict__ parent_pre,
                                            const float *__restrict__ parent_pos, int parent_pos_stride, int f,
                                            float offset_scale, float scale_factor, float *__restrict__ out_gauss,
                                            float *__restrict__ out_pre, long long R)
@@ -243,9 +244,11 @@ __global__ void surfel_cascade_pack_kernel(const float *__restrict__ res, const 
     const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= R) return;
     const long long pr = r / f;
+    // res_in_sequences: res holds one row per token of the [R/f, 1+f] micro-sequences (row 0 = the parent token)
+    const long long rr = res_in_sequences ? pr * (1 + f) + 1 + (r % f) : r;
     float p[13];
 #pragma unroll
-    for (int k = 0; k < 13; k++) p[k] = res[r * 13 + k];
+    for (int k = 0; k < 13; k++) p[k] = res[rr * 13 + k];
     float g[13];
 #pragma unroll
     for (int k = 0; k < 3; k++) g[k] = tanhf(p[k]) * offset_scale + parent_pos[pr * parent_pos_stride + k];
@@ -329,13 +332,13 @@ extern "C" int ga_micro_seq_build(const float *parents, int prev_f, const float 
     return last_err();
 }
 
-extern "C" int ga_surfel_cascade_pack(const float *res, const float *parent_pre, const float *parent_pos,
+extern "C" int ga_surfel_cascade_pack(const float *res, int res_in_sequences, const float *parent_pre, const float *parent_pos,
                                       int parent_pos_stride, int f, float offset_scale, float scale_factor,
                                       float *out_gauss13, float *out_pre, int64_t R, void *stream)
 {
     if (!res || !parent_pos || !out_gauss13 || R <= 0 || f <= 0 || parent_pos_stride < 3) return GA_ERR_BADARG;
     surfel_cascade_pack_kernel<<<(unsigned)((R + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-        res, parent_pre, parent_pos, parent_pos_stride, f, offset_scale, scale_factor, out_gauss13, out_pre, R);
+        res, res_in_sequences, parent_pre, parent_pos, parent_pos_stride, f, offset_scale, scale_factor, out_gauss13, out_pre, R);
     return last_err();
 }
 

@@ -229,10 +229,12 @@ int ga_micro_attention_bf16(const void *qkv, const float *qn_w, const float *kn_
  * s / prev_f of the previous stage's [S/prev_f, 1+prev_f, D] buffer), rows 1..f = queries [f, D] */
 int ga_micro_seq_build(const float *parents, int prev_f, const float *queries, float *seq, int64_t S, int f, int D,
                        void *stream);
-/* child r of parent r / f: pre = res[r] + parent_pre[r/f] (parent_pre NULL at the base level); xyz = tanh(res[r][0:3])
+/* child r of parent r / f: res row = r, or (res_in_sequences) row (r/f)(1+f) + 1 + r%f of the [R/f, 1+f] sequence
+ * layout; pre = res[row] + parent_pre[r/f] (parent_pre NULL at the base level); xyz = tanh(res[row][0:3])
  * * offset_scale + parent_pos[(r/f) * parent_pos_stride + 0..2]; other channels from pre: sigmoid | softplus *
  * scale_factor | normalise | 0.5 tanh + 0.5.  out_gauss13 [R,13] is rasteriser input; out_pre [R,13] feeds the next level */
-int ga_surfel_cascade_pack(const float *res, const float *parent_pre, const float *parent_pos, int parent_pos_stride,
+int ga_surfel_cascade_pack(const float *res, int res_in_sequences, const float *parent_pre, const float *parent_pos,
+                           int parent_pos_stride,
                            int f, float offset_scale, float scale_factor, float *out_gauss13, float *out_pre,
                            int64_t R, void *stream);
 int ga_silu_to_bf16(const float *x, void *y, int64_t n, void *stream);            /* y = bf16(silu(x)) */

@@ -25,7 +25,7 @@ def _env():
     L.ga_thin_linear.argtypes = [vp, vp, vp, i32, vp, vp, vp, i32, i32, i32, f32, vp]
     L.ga_micro_attention_bf16.argtypes = [vp, vp, vp, vp, i32, i32, i32, f32, vp]
     L.ga_micro_seq_build.argtypes = [vp, i32, vp, vp, i64, i32, i32, vp]
-    L.ga_surfel_cascade_pack.argtypes = [vp, vp, vp, i32, i32, f32, f32, vp, vp, i64, vp]
+    L.ga_surfel_cascade_pack.argtypes = [vp, i32, vp, vp, i32, i32, f32, f32, vp, vp, i64, vp]
     L.ga_silu_to_bf16.argtypes = [vp, vp, i64, vp]
     for n in ("ga_layernorm_modulate", "ga_thin_linear", "ga_micro_attention_bf16", "ga_micro_seq_build",
               "ga_surfel_cascade_pack", "ga_silu_to_bf16"):
@@ -115,18 +115,24 @@ def test_surfel_cascade_pack_matches_oracle_activations():
     xyz = (torch.rand(N, 3, device=dev) - 0.5) * 0.8
     g = torch.zeros(N, 13, device=dev)
     sf = float(act.scaling_factor)
-    assert L.ga_surfel_cascade_pack(_p(base_pre), None, _p(xyz), 3, 1, 0.45 * 0.5 * skip, sf, _p(g), None, N, st) == 0
+    assert L.ga_surfel_cascade_pack(_p(base_pre), 0, None, _p(xyz), 3, 1, 0.45 * 0.5 * skip, sf, _p(g), None, N, st) == 0
     ref = act.pack(act.offset(base_pre[:, :3]) * skip + xyz, base_pre)
     assert rel(g, ref) < 1e-5
     # child level: residual on the parent's pre-activation, offset from the parent's position (no skip weight)
     res = torch.randn(N * f, 13, device=dev) * 2
     gc, pre = torch.zeros(N * f, 13, device=dev), torch.zeros(N * f, 13, device=dev)
-    assert L.ga_surfel_cascade_pack(_p(res), _p(base_pre), _p(g), 13, f, 0.45 * 0.5, sf, _p(gc), _p(pre), N * f, st) == 0
+    assert L.ga_surfel_cascade_pack(_p(res), 0, _p(base_pre), _p(g), 13, f, 0.45 * 0.5, sf, _p(gc), _p(pre), N * f, st) == 0
     pre_ref = res.view(N, f, 13) + base_pre[:, None]
     pos_ref = act.offset(res.view(N, f, 13)[..., :3]) + g[:, None, :3]
     assert rel(pre, pre_ref.reshape(N * f, 13)) < 1e-6
     assert rel(gc, act.pack(pos_ref, pre_ref).reshape(N * f, 13)) < 1e-5
     assert torch.allclose(gc[:, 6:10].norm(dim=-1), torch.ones(N * f, device=dev), atol=1e-5)
+    # the same with the residuals still in the [N, 1+f] sequence layout (row 0 of every sequence is the parent token)
+    res_seq = torch.randn(N, 1 + f, 13, device=dev)
+    res_seq[:, 1:] = res.view(N, f, 13)
+    gc2 = torch.zeros_like(gc)
+    assert L.ga_surfel_cascade_pack(_p(res_seq), 1, _p(base_pre), _p(g), 13, f, 0.45 * 0.5, sf, _p(gc2), None, N * f, st) == 0
+    assert torch.equal(gc2, gc)
 
 
 def test_silu_to_bf16():
