@@ -349,6 +349,7 @@ def run_gpu(args):
                 dit_leg["frac_of_bf16_peak_sustained"] = dit_leg["tflops"] / float(pk.get("bf16_tflops_sustained", 1400.0))
                 dit_leg["deployed_L_N768"] = run_dit_deployed_leg(dev)
                 dit_leg["C4_L_N4096"] = run_dit_deployed_leg(dev, nfe=10, N=4096)
+                dit_leg["vae_decoder_N1"] = run_vae_decoder_leg(dev)
             except Exception as ex:                      # the raster metric is the headline; report, do not hide
                 dit_leg = {"error": repr(ex)}
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -459,6 +460,31 @@ def run_dit_leg(dev, steps_grid=50, reps=3):
             "e2e_samples_per_s": 1.0 / e2e_s, "launches_per_nfe": eng.launches_per_forward + 1,
             "kernels": {"self_attention": {"ms": 1e3 * t_attn, "tflops": fl_attn / t_attn / 1e12},
                         "gemm_mlp1_gelu": {"ms": 1e3 * t_gemm, "tflops": fl_gemm / t_gemm / 1e12}}}
+
+
+def run_vae_decoder_leg(dev, reps=5):
+    """SURVEY 8f row N1 at the deployed size: 768 latent tokens -> 73 728 surfels per sample (post_quant_conv, DiT2-B,
+    conv_sr, three cascaded up-samplers), random weights, batch 2.  Device time per sample and achieved TFLOP/s."""
+    import torch
+    from gaussiananything_b200.vae_decoder import SurfelDecoder, random_state_dict, decode_flops
+    dec = SurfelDecoder(random_state_dict(768, 12, 10, seed=0), 12, 12, device=dev)
+    B = 2
+    lat = torch.randn(B, 768, 10, device=dev)
+    xyz = (torch.rand(B, 768, 3, device=dev) - 0.5) * 0.8
+    for _ in range(2):
+        out = dec.decode(lat, xyz)
+    assert torch.isfinite(out["gaussians_upsampled_3"]).all()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(dev)
+    e0.record()
+    for _ in range(reps):
+        dec.decode(lat, xyz)
+    e1.record()
+    e1.synchronize()
+    ms = e0.elapsed_time(e1) / reps / B
+    return {"config": "N1: VAE decoder, 768 tokens x 768, DiT2-B + cascade 8*4*3 -> 73728 surfels/sample, batch 2, bf16",
+            "ms_per_sample": ms, "samples_per_s": 1e3 / ms, "tflops": decode_flops(768, 12) / (ms * 1e-3) / 1e12,
+            "surfels_per_sample": 73728}
 
 
 def run_dit_deployed_leg(dev, nfe=20, N=768):

@@ -203,3 +203,60 @@ class SurfelDecoder:
         out["pos"] = out["gaussians"][..., :3]
         out["gaussians_base_opa"] = out["gaussians_base"][..., 3:4]
         return out
+
+
+def random_state_dict(D=768, depth=12, zc=10, seed=0, device="cpu"):
+    """A state_dict with the reference decoder's key layout and shapes (vit_triplane.py:1316-1345,1614-1640) and
+    random weights -- for benchmarks and size tests (there is no network for checkpoints)."""
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+
+    def lin(name, n_out, n_in, bias=True):
+        sd[name + ".weight"] = torch.randn(n_out, n_in, generator=g) / n_in ** 0.5
+        if bias:
+            sd[name + ".bias"] = torch.randn(n_out, generator=g) * 0.02
+
+    def attn_mlp(pa, pm):
+        lin(pa + "qkv", 3 * D, D)
+        lin(pa + "proj", D, D)
+        sd[pa + "q_norm.weight"] = 1.0 + 0.1 * torch.randn(64, generator=g)
+        sd[pa + "k_norm.weight"] = 1.0 + 0.1 * torch.randn(64, generator=g)
+        sd[pm + "mlp.0.weight"] = torch.randn(4 * D, D, generator=g) / D ** 0.5
+        sd[pm + "mlp.1.bias"] = torch.randn(4 * D, generator=g) * 0.02
+        sd[pm + "mlp.2.weight"] = torch.randn(D, 4 * D, generator=g) / (4 * D) ** 0.5
+        sd[pm + "mlp.3.bias"] = torch.randn(D, generator=g) * 0.02
+
+    sd["vit_decoder.pos_embed"] = torch.randn(1, D, D, generator=g) * 0.02          # token count == width (reference)
+    for l in range(depth):
+        p = "vit_decoder.blocks.%d." % l
+        attn_mlp(p + "attn.", p + "mlp.")
+        sd[p + "adaLN_modulation.1.weight"] = torch.randn(6 * D, D, generator=g) * 0.02
+        sd[p + "adaLN_modulation.1.bias"] = torch.randn(6 * D, generator=g) * 0.02
+    q = "superresolution."
+    lin(q + "post_quant_conv.fc1", zc, zc)
+    lin(q + "post_quant_conv.fc2", D, zc)
+    sd[q + "conv_sr.gaussian_pred.1.weight"] = torch.randn(13, D, generator=g) * 0.02
+    sd[q + "conv_sr.gaussian_pred.1.bias"] = torch.randn(13, generator=g) * 0.1
+    for (name, f), nl in zip(SurfelDecoder.CASCADE, (depth // 6 if depth == 12 else 2, 1, 1)):
+        p = q + name + "."
+        sd[p + "latent_embedding"] = torch.randn(1, f, D, generator=g)
+        sd[p + "gaussian_residual_pred.norm.weight"] = torch.ones(D)
+        sd[p + "gaussian_residual_pred.norm.bias"] = torch.zeros(D)
+        sd[p + "gaussian_residual_pred.fn.weight"] = torch.randn(13, D, generator=g) * 0.02
+        sd[p + "gaussian_residual_pred.fn.bias"] = torch.randn(13, generator=g) * 0.02
+        for l in range(nl):
+            t = "%stransformer.layers.%d." % (p, l)
+            attn_mlp(t + "0.fn.", t + "1.fn.")
+            for n in ("0.norm.", "1.norm."):
+                sd[t + n + "weight"] = 1.0 + 0.1 * torch.randn(D, generator=g)
+                sd[t + n + "bias"] = torch.randn(D, generator=g) * 0.02
+    return {k: v.to(device) for k, v in sd.items()}
+
+
+def decode_flops(D=768, depth=12, N=None):
+    """Multiply-add x 2 count of one sample (tools/n1_cost.py): DiT2 blocks + the per-token adaLN GEMM + three
+    up-sampler stages of depth (2 if depth != 12 else depth // 6), 1, 1."""
+    N = D if N is None else N
+    blk = lambda Ls: 2 * Ls * D * (3 * D + D + 8 * D) + 4 * Ls * Ls * D
+    d1 = depth // 6 if depth == 12 else 2
+    return (depth * (blk(N) + 2 * N * D * 6 * D) + N * d1 * blk(9) + N * 8 * blk(5) + N * 32 * blk(4))

@@ -58,3 +58,25 @@ def test_decoded_surfels_feed_the_rasteriser():
     cp = torch.tensor(pos, device=dev)[None, None].expand(B, 1, 3).contiguous()
     img = GaussianRenderer2DGS(64, 3, {}).render(surf, cv, cvp, cp, tanfov)
     assert torch.isfinite(img["image"]).all() and float(img["alpha"].max()) > 0.05
+
+
+def test_surfel_decoder_deployed_size_properties():
+    """Deployed size (768 tokens, width 768, 12 blocks, cascade 8*4*3 -> 73 728 surfels per sample), random weights:
+    the oracle cannot run this in seconds, so size-independent properties: shapes, finite, valid surfels, same bits on
+    a second run, batch items independent."""
+    from gaussiananything_b200.vae_decoder import SurfelDecoder, random_state_dict
+    dev = torch.device("cuda:0")
+    dec = SurfelDecoder(random_state_dict(768, 12, 10, seed=1), 12, 12, device=dev)
+    torch.manual_seed(0)
+    lat = torch.randn(2, 768, 10, device=dev)
+    xyz = (torch.rand(2, 768, 3, device=dev) - 0.5) * 0.8
+    out = dec.decode(lat, xyz)
+    s = out["gaussians_upsampled_3"]
+    assert s.shape == (2, 73728, 13) and out["gaussians"].shape == (2, 6144, 13)
+    assert torch.isfinite(s).all()
+    assert torch.allclose(s[..., 6:10].norm(dim=-1), torch.ones(s.shape[:2], device=dev), atol=1e-5)
+    assert (s[..., 3] >= 0).all() and (s[..., 3] <= 1).all() and (s[..., 4:6] > 0).all()
+    out2 = dec.decode(lat, xyz)
+    assert torch.equal(out2["gaussians_upsampled_3"], s)
+    out3 = dec.decode(lat.flip(0).contiguous(), xyz.flip(0).contiguous())
+    assert rel(out3["gaussians_upsampled_3"].flip(0), s) < 1e-5

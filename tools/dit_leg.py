@@ -10,5 +10,7 @@ import bench  # noqa: E402
 dev = torch.device("cuda:0")
 print(json.dumps(bench.run_dit_leg(dev)))
 print(json.dumps(bench.run_dit_deployed_leg(dev)))
+if "n1" in sys.argv:
+    print(json.dumps(bench.run_vae_decoder_leg(dev)))
 if "c4" in sys.argv:
     print(json.dumps(bench.run_dit_deployed_leg(dev, nfe=10, N=4096)))
