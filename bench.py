@@ -349,7 +349,10 @@ def run_gpu(args):
                 dit_leg["frac_of_bf16_peak_sustained"] = dit_leg["tflops"] / float(pk.get("bf16_tflops_sustained", 1400.0))
                 dit_leg["deployed_L_N768"] = run_dit_deployed_leg(dev)
                 dit_leg["C4_L_N4096"] = run_dit_deployed_leg(dev, nfe=10, N=4096)
-                dit_leg["vae_decoder_N1"] = run_vae_decoder_leg(dev)
+                try:
+                    dit_leg["vae_decoder_N1"] = run_vae_decoder_leg(dev)
+                except Exception as ex:                  # never let the newest leg take the DiT numbers down with it
+                    dit_leg["vae_decoder_N1"] = {"error": repr(ex)}
             except Exception as ex:                      # the raster metric is the headline; report, do not hide
                 dit_leg = {"error": repr(ex)}
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
