@@ -17,4 +17,20 @@ timeout 300 ncu --set full --clock-control none --import-source on -k regex:rend
 timeout 200 ncu --set full --clock-control none --import-source on -k regex:gemm -s 3 -c 1 -o gpurun_out/final_gemm_mlp1 \
     python tools/one_gemm.py 4096 3072 768 128 gelu > /dev/null 2>&1
 bash profiles/run_profile_attn.sh > /dev/null 2>&1; mv gpurun_out/prof_attn.ncu-rep gpurun_out/final_attn.ncu-rep
+# row N1 (VAE decoder): launch list of one decode at the deployed size + the micro-attention kernel in full
+cat > /tmp/n1_prof.py <<'PY'
+import sys, torch
+sys.path.insert(0, ".")
+from gaussiananything_b200.vae_decoder import SurfelDecoder, random_state_dict
+dev = torch.device("cuda:0")
+dec = SurfelDecoder(random_state_dict(768, 12, 10, seed=0), 12, 12, device=dev)
+lat = torch.randn(2, 768, 10, device=dev); xyz = (torch.rand(2, 768, 3, device=dev) - 0.5) * 0.8
+for _ in range(2):
+    dec.decode(lat, xyz)
+torch.cuda.synchronize()
+PY
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 2000 --csv --log-file gpurun_out/launches_n1.csv \
+    python /tmp/n1_prof.py > /dev/null 2>&1
+timeout 200 ncu --set full --clock-control none --import-source on -k regex:micro_attention -s 3 -c 1 -o gpurun_out/final_micro_attn \
+    python /tmp/n1_prof.py > /dev/null 2>&1
 ls -la gpurun_out | tail -15
