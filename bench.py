@@ -392,7 +392,7 @@ def run_dit_leg(dev, steps_grid=50, reps=3):
     L, D, H, N, M, Dc, Cin = 12, 768, 12, 2048, 1369, 1024, 3
     m = dit.DiT_models["DiT-PixArt-PCD-CLAY-B"](input_size=32, num_classes=0, learn_sigma=False, in_channels=Cin,
                                                 context_dim=Dc, roll_out=True, pooling_ctx_dim=768)
-    m.randomize_zero_init_().to(dev)
+    m.randomize_zero_init_().to(dev).eval()
     B = 2                                              # one sample, CFG doubles the batch
     h_z = torch.randn(1, N, Cin).pin_memory()
     h_ctx = torch.randn(1, M, Dc).pin_memory()
@@ -503,7 +503,7 @@ def run_dit_deployed_leg(dev, nfe=20, N=768):
     for name, cin, stage2 in (("DiT-PixArt-PCD-CLAY-L", 3, False), ("DiT-PixArt-PCD-CLAY-stage2-L", 10, True)):
         m = dit.DiT_models[name](input_size=32, num_classes=0, learn_sigma=False, in_channels=cin, context_dim=Dc,
                                  roll_out=True, pooling_ctx_dim=768)
-        m.randomize_zero_init_().to(dev)
+        m.randomize_zero_init_().to(dev).eval()
         z = torch.randn(B, N, cin, device=dev)
         ctx = {"img_crossattn": torch.randn(B, M, Dc, device=dev), "img_vector": torch.randn(B, Dc, device=dev)}
         if stage2:

@@ -25,6 +25,7 @@
 // write bf16 P straight into TMEM (tcgen05.st, 64 columns) and P*V takes its A operand from there
 // (tcgen05.mma [d], [a_tmem], b_desc): 80 KB per block, the kernel is MUFU-bound again.
 #include "../../include/ga_b200.h"
+#include "device_once.cuh"
 #include "sm100_ptx.cuh"
 
 using namespace sm100;
@@ -425,13 +426,12 @@ extern "C" int ga_attention_bf16(const void *Q, const void *K, const void *Vt, v
     if (!Q || !K || !Vt || !out || batch <= 0 || heads <= 0 || Nq <= 0 || Nk <= 0) return GA_ERR_BADARG;
     if (pitch_q < Nq || pitch_k < Nk || pitch_k % 128 != 0) return GA_ERR_BADARG;
     const uint64_t BH = (uint64_t)batch * heads;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static GaPerDevice attr_set;
+    if (ga_first_use_on_device(attr_set)) {
         cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemAttn);
         if (e != cudaSuccess) return (int)e;
         e = cudaFuncSetAttribute(attn_fwd_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemAttn);
         if (e != cudaSuccess) return (int)e;
-        attr_set = true;
     }
     // static-bound softmax only while exp(-2*bound) stays far from the fp32/bf16 underflow range
     const bool use_static = score_bound > 0.f && score_bound <= 40.f;

@@ -12,6 +12,7 @@
 // smem ring of kStages {A 128x64, W BNx64} bf16 tiles with full/empty mbarriers; the TMEM accumulator is
 // double buffered (acc_full/acc_empty) so the epilogue of one tile overlaps the main loop of the next.
 #include "../../include/ga_b200.h"
+#include "device_once.cuh"
 #include "sm100_ptx.cuh"
 
 using namespace sm100;
@@ -604,29 +605,18 @@ int ga_make_tmap_bf16(CUtensorMap *map, const void *ptr, uint64_t rows, uint64_t
     return r == CUDA_SUCCESS ? 0 : 1000 + (int)r;
 }
 
-static int sm_count()
-{
-    static int num_sms = 0;
-    if (!num_sms) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-        if (num_sms <= 0) num_sms = 148;
-    }
-    return num_sms;
-}
+static int sm_count() { return ga_sm_count(); }
 
 template <int BN, int CS, int MODE>
 static int launch_gemm_mode(const CUtensorMap &ta, const CUtensorMap &tb, const GaGemmEpilogue &ep, int M, int N, int K,
                             cudaStream_t s)
 {
     using Cfg = GemmCfg<BN>;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static GaPerDevice attr_set;
+    if (ga_first_use_on_device(attr_set)) {
         cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tn_kernel<BN, CS, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              Cfg::kSmem);
         if (e != cudaSuccess) return (int)e;
-        attr_set = true;
     }
     const int num_m = (M + BM - 1) / BM, num_n = (N + BN - 1) / BN;
     const int items = ((num_m + CS - 1) / CS) * num_n;              // work items per cluster
@@ -667,12 +657,11 @@ static int launch_gemm_pair_mode(const CUtensorMap &ta, const CUtensorMap &tb, c
                                  cudaStream_t s)
 {
     using Cfg = PairCfg<BN>;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static GaPerDevice attr_set;
+    if (ga_first_use_on_device(attr_set)) {
         cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tn_pair_kernel<BN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              Cfg::kSmem);
         if (e != cudaSuccess) return (int)e;
-        attr_set = true;
     }
     const int num_m = (M + BM - 1) / BM, num_n = (N + BN - 1) / BN;
     const int items = ((num_m + 1) / 2) * num_n;

@@ -31,6 +31,22 @@ extern "C" int ga_profile_read(float *ms, int n)
     return 5;
 }
 
+static int g_radius_formula = GA_RADIUS_FORMULA, g_quat_norm_grad = GA_QUAT_NORM_GRAD;
+
+extern "C" int ga_raster_set_variant(int radius_formula, int quat_norm_grad)
+{
+    g_radius_formula = radius_formula ? 1 : 0;
+    g_quat_norm_grad = quat_norm_grad ? 1 : 0;
+    return 0;
+}
+
+extern "C" int ga_raster_get_variant(int *radius_formula, int *quat_norm_grad)
+{
+    if (!radius_formula || !quat_norm_grad) return GA_ERR_BADARG;
+    *radius_formula = g_radius_formula; *quat_norm_grad = g_quat_norm_grad;
+    return 0;
+}
+
 static int make_dims(int batch, int P, int views, int H, int W, float scale_modifier,
                      int64_t max_instances, RasterDims *d)
 {
@@ -42,6 +58,7 @@ static int make_dims(int batch, int P, int views, int H, int W, float scale_modi
     d->T = d->gx * d->gy;
     d->scale_modifier = scale_modifier;
     d->max_instances = max_instances;
+    d->radius_formula = g_radius_formula; d->quat_norm_grad = g_quat_norm_grad;
     if (d->gx > 255 || d->gy > 255) return GA_ERR_SIZE;
     if ((int64_t)d->NV * P > 0x7fffffffLL || max_instances > 0xfffffff0LL) return GA_ERR_SIZE;
     if (d->NV > 65535) return GA_ERR_SIZE;

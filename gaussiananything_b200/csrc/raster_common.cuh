@@ -26,7 +26,17 @@ struct RasterDims {
     int H, W, gx, gy, T;       // T = gx*gy tiles per image
     float scale_modifier;
     int64_t max_instances;
+    // the two unpinned judgement calls of the restatement, switchable so that pinning against
+    // upstream is a flip of the defaults below; ga_raster_set_variant() overrides them at run time (tests)
+    int radius_formula;        // 0: ceil(max(ex, ey, 3*FilterSize))   1: ceil(3*max(ex, ey, FilterSize))
+    int quat_norm_grad;        // 0: quaternion vjp not chained through q/|q| (upstream)   1: chained
 };
+#ifndef GA_RADIUS_FORMULA
+#define GA_RADIUS_FORMULA 0
+#endif
+#ifndef GA_QUAT_NORM_GRAD
+#define GA_QUAT_NORM_GRAD 0
+#endif
 
 struct RasterWs {
     int32_t *status;

@@ -110,7 +110,8 @@ preprocess_kernel(RasterDims d, RasterWs ws, const float *__restrict__ gauss13,
                 float hx0 = cx * cx - ((f0 * (Tu[0] * Tu[0]) + f1 * (Tu[1] * Tu[1])) + f2 * (Tu[2] * Tu[2]));
                 float hy0 = cy * cy - ((f0 * (Tv[0] * Tv[0]) + f1 * (Tv[1] * Tv[1])) + f2 * (Tv[2] * Tv[2]));
                 float ex = sqrtf(fmaxf(1e-4f, hx0)), ey = sqrtf(fmaxf(1e-4f, hy0));
-                float radius = ceilf(fmaxf(fmaxf(ex, ey), GA_CUTOFF * GA_FILTER_SIZE));
+                float radius = d.radius_formula == 0 ? ceilf(fmaxf(fmaxf(ex, ey), GA_CUTOFF * GA_FILTER_SIZE))
+                                                     : ceilf(GA_CUTOFF * fmaxf(fmaxf(ex, ey), GA_FILTER_SIZE));
                 int mr = (int)radius;
                 int x0 = min(d.gx, max(0, (int)((cx - (float)mr) / (float)GA_BLOCK_X)));
                 int y0 = min(d.gy, max(0, (int)((cy - (float)mr) / (float)GA_BLOCK_Y)));
@@ -275,6 +276,10 @@ preprocess_bwd_kernel(RasterDims d, RasterWs ws, const float *__restrict__ gauss
     float gxq = 2 * (-2 * x * (dR[1][1] + dR[2][2]) + y * (dR[1][0] + dR[0][1]) + z * (dR[2][0] + dR[0][2]) + w * (dR[2][1] - dR[1][2]));
     float gyq = 2 * (x * (dR[1][0] + dR[0][1]) - 2 * y * (dR[0][0] + dR[2][2]) + z * (dR[2][1] + dR[1][2]) + w * (dR[0][2] - dR[2][0]));
     float gzq = 2 * (x * (dR[2][0] + dR[0][2]) + y * (dR[2][1] + dR[1][2]) - 2 * z * (dR[0][0] + dR[1][1]) + w * (dR[1][0] - dR[0][1]));
+    if (d.quat_norm_grad) {          // chain through q_hat = q / |q|: g_raw = (g - q_hat (q_hat . g)) / |q|
+        const float dot = w * gw + x * gxq + y * gyq + z * gzq;
+        gw = (gw - w * dot) * s; gxq = (gxq - x * dot) * s; gyq = (gyq - y * dot) * s; gzq = (gzq - z * dot) * s;
+    }
     float *o = grad_gauss13 + ((size_t)b * d.P + i) * 13;
     o[0] = gm[0]; o[1] = gm[1]; o[2] = gm[2];
     o[3] = gop;

@@ -13,6 +13,7 @@
 //    gradient over the warp with shuffles, over the CTA in shared memory, and
 //    issues one global atomic per (tile, surfel, component).
 #include "raster_common.cuh"
+#include "device_once.cuh"
 #include <cstdlib>
 
 #define CHUNK 256
@@ -551,12 +552,11 @@ cudaError_t ga_launch_render_bwd(const RasterDims &d, const RasterWs &w, const f
                                  const float *dL_dcolor, const float *dL_dallmap,
                                  float *grad_acc, cudaStream_t s)
 {
-    static bool attr_set = false;
-    if (!attr_set) {
+    static GaPerDevice attr_set;
+    if (ga_first_use_on_device(attr_set)) {
         cudaError_t e = cudaFuncSetAttribute(render_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)sizeof(BwdSmem));
         if (e != cudaSuccess) return e;
-        attr_set = true;
     }
     dim3 grid(d.gx, d.gy, d.NV);
     render_bwd_kernel<<<grid, 256, sizeof(BwdSmem), s>>>(d, w, bg, dL_dcolor, dL_dallmap, grad_acc);

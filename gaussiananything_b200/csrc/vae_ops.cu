@@ -9,6 +9,7 @@
 // /root/reference/dit/dit_decoder.py:15-42, /root/reference/nsr/srt/layers.py:82-90,146-186 and
 // /root/reference/vit/vision_transformer.py:215-303; the checker is oracle/vae_decoder_oracle.py.
 #include "../../include/ga_b200.h"
+#include "device_once.cuh"
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
@@ -307,12 +308,11 @@ extern "C" int ga_micro_attention_bf16(const void *qkv, const float *qn_w, const
                                        int H, float eps, void *stream)
 {
     if (!qkv || !qn_w || !kn_w || !out || S <= 0 || L <= 0 || L > kMicroL || H <= 0) return GA_ERR_BADARG;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static GaPerDevice attr_set;
+    if (ga_first_use_on_device(attr_set)) {
         cudaError_t e = cudaFuncSetAttribute(micro_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              kMicroWarps * kMicroSmemPerWarp);
         if (e != cudaSuccess) return (int)e;
-        attr_set = true;
     }
     const long long items = (long long)S * H;
     micro_attention_kernel<<<(unsigned)((items + kMicroWarps - 1) / kMicroWarps), 32 * kMicroWarps,

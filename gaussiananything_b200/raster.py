@@ -80,6 +80,11 @@ def forward_raw(gauss13, viewmats, projmats, bg, H, W, scale_modifier=1.0, max_i
     viewmats = viewmats.reshape(B * V, 16).contiguous().float()
     projmats = projmats.reshape(B * V, 16).contiguous().float()
     bg = bg.to(device=dev, dtype=torch.float32).contiguous()
+    with torch.cuda.device(dev):           # launches go to the tensors' device, not the process's current one
+        return _forward_on_device(lib, dev, gauss13, viewmats, projmats, bg, B, P, V, H, W, scale_modifier, max_instances)
+
+
+def _forward_on_device(lib, dev, gauss13, viewmats, projmats, bg, B, P, V, H, W, scale_modifier, max_instances):
     key = (B, P, V, H, W)
     if max_instances is None:
         max_instances = _capacity_hint.get(key, 4 * B * V * P + 1024)
@@ -117,14 +122,15 @@ def backward_raw(state, grad_color, grad_allmap):
     grad_color = grad_color.contiguous().float()
     grad_allmap = grad_allmap.contiguous().float()
     nbytes = lib.ga_raster_backward_scratch_bytes(B, P, V)
-    scratch = torch.empty(nbytes, device=dev, dtype=torch.uint8)
-    grad = torch.empty(B, P, 13, device=dev, dtype=torch.float32)
-    rc = lib.ga_raster_backward(_ptr(state["gauss13"]), B, P, V, _ptr(state["viewmats"]),
-                                _ptr(state["projmats"]), _ptr(state["bg"]), H, W,
-                                state["scale_modifier"], _ptr(state["radii"]),
-                                _ptr(grad_color), _ptr(grad_allmap),
-                                _ptr(state["ws"]), state["L"].total_bytes, state["max_instances"],
-                                _ptr(scratch), nbytes, _ptr(grad), _stream(dev))
+    with torch.cuda.device(dev):
+        scratch = torch.empty(nbytes, device=dev, dtype=torch.uint8)
+        grad = torch.empty(B, P, 13, device=dev, dtype=torch.float32)
+        rc = lib.ga_raster_backward(_ptr(state["gauss13"]), B, P, V, _ptr(state["viewmats"]),
+                                    _ptr(state["projmats"]), _ptr(state["bg"]), H, W,
+                                    state["scale_modifier"], _ptr(state["radii"]),
+                                    _ptr(grad_color), _ptr(grad_allmap),
+                                    _ptr(state["ws"]), state["L"].total_bytes, state["max_instances"],
+                                    _ptr(scratch), nbytes, _ptr(grad), _stream(dev))
     _lib.check(rc, "ga_raster_backward")
     return grad
 
@@ -133,13 +139,17 @@ class _RasterizeSurfelsBatched(torch.autograd.Function):
     @staticmethod
     def forward(ctx, gauss13, viewmats, projmats, bg, H, W, scale_modifier):
         color, allmap, radii, state = forward_raw(gauss13, viewmats, projmats, bg, H, W, scale_modifier)
+        # the tensors the backward re-reads go through save_for_backward, so an in-place change between forward
+        # and backward is detected by autograd's version check instead of silently giving wrong gradients
+        ctx.save_for_backward(state.pop("gauss13"), state.pop("viewmats"), state.pop("projmats"))
         ctx.state = state
         ctx.mark_non_differentiable(radii)
         return color, allmap, radii
 
     @staticmethod
     def backward(ctx, grad_color, grad_allmap, _grad_radii):
-        grad = backward_raw(ctx.state, grad_color, grad_allmap)
+        g13, vm, pm = ctx.saved_tensors
+        grad = backward_raw(dict(ctx.state, gauss13=g13, viewmats=vm, projmats=pm), grad_color, grad_allmap)
         return grad, None, None, None, None, None, None
 
 
@@ -164,8 +174,10 @@ class _RenderPost(torch.autograd.Function):
         depth = torch.empty(B, V, 1, H, W, device=dev)
         normal = torch.empty(B, V, 3, H, W, device=dev)
         dist = torch.empty(B, V, 1, H, W, device=dev)
-        _lib.check(lib.ga_render_post_forward(_ptr(color), _ptr(allmap), _ptr(vm), B * V, H, W, _ptr(image), _ptr(alpha),
-                                              _ptr(depth), _ptr(normal), _ptr(dist), _stream(dev)), "ga_render_post_forward")
+        with torch.cuda.device(dev):
+            _lib.check(lib.ga_render_post_forward(_ptr(color), _ptr(allmap), _ptr(vm), B * V, H, W, _ptr(image),
+                                                  _ptr(alpha), _ptr(depth), _ptr(normal), _ptr(dist), _stream(dev)),
+                       "ga_render_post_forward")
         ctx.save_for_backward(color, allmap, vm)
         return image, alpha, depth, normal, dist
 
@@ -180,8 +192,9 @@ class _RenderPost(torch.autograd.Function):
         g_allmap = torch.empty_like(allmap)
         null = C.c_void_p(0)
         ptrs = [null if g is None else _ptr(g) for g in gs]
-        _lib.check(lib.ga_render_post_backward(_ptr(color), _ptr(allmap), _ptr(vm), B * V, H, W, *ptrs, _ptr(g_color),
-                                               _ptr(g_allmap), _stream(dev)), "ga_render_post_backward")
+        with torch.cuda.device(dev):
+            _lib.check(lib.ga_render_post_backward(_ptr(color), _ptr(allmap), _ptr(vm), B * V, H, W, *ptrs, _ptr(g_color),
+                                                   _ptr(g_allmap), _stream(dev)), "ga_render_post_backward")
         return g_color, g_allmap, None
 
 

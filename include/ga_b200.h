@@ -111,6 +111,18 @@ int ga_render_post_backward(const float *color, const float *allmap, const float
                             int H, int W, const float *g_image, const float *g_alpha, const float *g_depth,
                             const float *g_normal, const float *g_dist, float *g_color, float *g_allmap, void *stream);
 
+/*
+ * The two judgement calls of the (parity-unpinned) restatement of upstream's preprocess stage, switchable at run
+ * time; the process-wide defaults are the compile-time macros GA_RADIUS_FORMULA / GA_QUAT_NORM_GRAD (both 0):
+ *   radius_formula 0: radius = ceil(max(extent.x, extent.y, 3*FilterSize))   1: ceil(3*max(extent.x, extent.y, FilterSize))
+ *   quat_norm_grad 0: dL/dquat is the vjp at q/|q|, not chained through the normalisation   1: chained
+ * Replaces nothing in the reference (upstream hard-codes its choice); exists so that pinning against
+ * github.com/hbb1/diff-surfel-rasterization forward.cu / backward.cu is a one-line flip.  oracle/surfel_oracle.c
+ * has the same switch (so_set_variant).  Affects calls made after it returns.
+ */
+int ga_raster_set_variant(int radius_formula, int quat_norm_grad);
+int ga_raster_get_variant(int *radius_formula, int *quat_norm_grad);
+
 /* Bytes of scratch the backward needs (gradient accumulators). */
 size_t ga_raster_backward_scratch_bytes(int batch, int P, int views);
 

@@ -58,6 +58,32 @@ int so_set_num_threads(int n)
 #define FILTER_INV_SQUARE 2.0f
 #define CUTOFF 3.0f
 
+/*
+ * The two judgement calls of this (unpinned) restatement are switchable, here and in the CUDA path
+ * (ga_raster_set_variant, include/ga_b200.h), so pinning against upstream is a one-line flip of a default:
+ *   radius formula       0: ceil(max(max(ex, ey), 3 * FilterSize))       (default; our reading of upstream forward.cu)
+ *                        1: ceil(3 * max(max(ex, ey), FilterSize))       (SURVEY.md App. A item 5's alternative)
+ *   quaternion gradient  0: vjp at the normalised quaternion, NOT chained through the normalisation (default)
+ *                        1: chained through q / |q|
+ * Both are no-ops for the reference's call except (radius) the tile rectangle of sub-pixel surfels.
+ */
+#ifndef SO_RADIUS_FORMULA
+#define SO_RADIUS_FORMULA 0
+#endif
+#ifndef SO_QUAT_NORM_GRAD
+#define SO_QUAT_NORM_GRAD 0
+#endif
+static int g_radius_formula = SO_RADIUS_FORMULA, g_quat_norm_grad = SO_QUAT_NORM_GRAD;
+void so_set_variant(int radius_formula, int quat_norm_grad)
+{
+    g_radius_formula = radius_formula ? 1 : 0;
+    g_quat_norm_grad = quat_norm_grad ? 1 : 0;
+}
+void so_get_variant(int *radius_formula, int *quat_norm_grad)
+{
+    *radius_formula = g_radius_formula; *quat_norm_grad = g_quat_norm_grad;
+}
+
 static inline int imin(int a, int b) { return a < b ? a : b; }
 static inline int imax(int a, int b) { return a > b ? a : b; }
 
@@ -173,7 +199,8 @@ void so_preprocess(int P, const float *means3D, const float *opacities,
         float hx0 = cx * cx - ((f0 * (Tu[0] * Tu[0]) + f1 * (Tu[1] * Tu[1])) + f2 * (Tu[2] * Tu[2]));
         float hy0 = cy * cy - ((f0 * (Tv[0] * Tv[0]) + f1 * (Tv[1] * Tv[1])) + f2 * (Tv[2] * Tv[2]));
         float ex = sqrtf(fmaxf(1e-4f, hx0)), ey = sqrtf(fmaxf(1e-4f, hy0));
-        float radius = ceilf(fmaxf(fmaxf(ex, ey), CUTOFF * FILTER_SIZE));
+        float radius = g_radius_formula == 0 ? ceilf(fmaxf(fmaxf(ex, ey), CUTOFF * FILTER_SIZE))
+                                             : ceilf(CUTOFF * fmaxf(fmaxf(ex, ey), FILTER_SIZE));
 
         int x0, y0, x1, y1;
         get_rect(cx, cy, (int)radius, gx, gy, &x0, &y0, &x1, &y1);
@@ -548,6 +575,10 @@ void so_preprocess_backward(int P, const float *means3D, const float *scales,
         double gxq = 2 * (-2 * x * (dR[1][1] + dR[2][2]) + y * (dR[1][0] + dR[0][1]) + z * (dR[2][0] + dR[0][2]) + w * (dR[2][1] - dR[1][2]));
         double gyq = 2 * (x * (dR[1][0] + dR[0][1]) - 2 * y * (dR[0][0] + dR[2][2]) + z * (dR[2][1] + dR[1][2]) + w * (dR[0][2] - dR[2][0]));
         double gzq = 2 * (x * (dR[2][0] + dR[0][2]) + y * (dR[2][1] + dR[1][2]) - 2 * z * (dR[0][0] + dR[1][1]) + w * (dR[1][0] - dR[0][1]));
+        if (g_quat_norm_grad) {          /* chain through q_hat = q / |q|: g_raw = (g - q_hat (q_hat . g)) / |q| */
+            const double dot = w * gw + x * gxq + y * gyq + z * gzq;
+            gw = (gw - w * dot) * s; gxq = (gxq - x * dot) * s; gyq = (gyq - y * dot) * s; gzq = (gzq - z * dot) * s;
+        }
         dL_drots[4 * i] += gw; dL_drots[4 * i + 1] += gxq; dL_drots[4 * i + 2] += gyq; dL_drots[4 * i + 3] += gzq;
     }
 }

@@ -23,8 +23,14 @@ NEAR_N, FAR_N = 0.2, 100.0
 FILTER_SIZE, FILTER_INV_SQUARE = 0.707106, 2.0
 
 
+RADIUS_FORMULA = 0        # see oracle/surfel_oracle.c: 0 = ceil(max(ex, ey, 3 f)), 1 = ceil(3 max(ex, ey, f))
+QUAT_NORM_GRAD = 0        # 0 = normalisation factor is a constant (detached), 1 = autograd chains through it
+
+
 def _quat_to_R(q):
-    s = (1.0 / q.norm(dim=-1, keepdim=True)).detach()
+    s = 1.0 / q.norm(dim=-1, keepdim=True)
+    if not QUAT_NORM_GRAD:
+        s = s.detach()
     w, x, y, z = (q * s).unbind(-1)
     R = torch.stack([
         1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y),
@@ -71,8 +77,12 @@ def rasterize(means3D, opacities, scales, rotations, colors, viewmatrix, projmat
     hy0 = cy * cy - (f * Tv * Tv).sum(-1)
     ex = torch.sqrt(torch.clamp(hx0, min=1e-4))
     ey = torch.sqrt(torch.clamp(hy0, min=1e-4))
-    radius = torch.ceil(torch.maximum(torch.maximum(ex, ey),
-                                      torch.tensor(3.0 * FILTER_SIZE, dtype=dt))).detach()
+    if RADIUS_FORMULA == 0:
+        radius = torch.ceil(torch.maximum(torch.maximum(ex, ey),
+                                          torch.tensor(3.0 * FILTER_SIZE, dtype=dt))).detach()
+    else:
+        radius = torch.ceil(3.0 * torch.maximum(torch.maximum(ex, ey),
+                                                torch.tensor(FILTER_SIZE, dtype=dt))).detach()
     gx, gy = (W + 15) // 16, (H + 15) // 16
     ri = radius.to(torch.int64).to(dt)
 

@@ -1,7 +1,7 @@
 """Shared helpers for the parity tests (scene builders + metrics)."""
 import numpy as np
 
-from oracle import surfel_oracle as so
+from tools import synth as so          # scene / camera builders: numpy only (the oracle is imported lazily below)
 
 
 def rel_l2(a, b):
@@ -29,5 +29,6 @@ def scene(P, seed, scale_boost=1.0, smin=None, smax=None):
 
 
 def oracle_view(g, view, proj, bg, H, W, scale_modifier=1.0):
+    from oracle import surfel_oracle as so
     return so.rasterize(g[:, 0:3], g[:, 3:4], g[:, 4:6], g[:, 6:10], g[:, 10:13], view, proj, bg, H, W,
                         scale_modifier)

@@ -194,7 +194,7 @@ def _build(g, dev):
     missing, unexpected = m.load_state_dict(g["sd"], strict=False)
     assert not unexpected
     assert all(any(u in k for u in ("clip_spatial_proj", "cap_embedder", "attention_y_norm")) for k in missing), missing
-    return m.to(dev)
+    return m.to(dev).eval()
 
 
 @pytest.mark.parametrize("name", ["dit_stage1_small", "dit_stage2_small", "dit_stage2_concat_small"])
@@ -242,7 +242,7 @@ def test_dit_b_full_size_properties():
     torch.manual_seed(0)
     m = dit.DiT_models["DiT-PixArt-PCD-CLAY-B"](input_size=32, num_classes=0, learn_sigma=False, in_channels=3,
                                                 context_dim=1024, roll_out=True, pooling_ctx_dim=768)
-    m.randomize_zero_init_().to(dev)
+    m.randomize_zero_init_().to(dev).eval()
     B, N, M = 2, 2048, 1369
     x = torch.randn(B, N, 3, device=dev)
     t = torch.rand(B, device=dev)
@@ -268,7 +268,7 @@ def test_dit_l_c4_size_properties():
     for name, cin, stage2 in (("DiT-PixArt-PCD-CLAY-L", 3, False), ("DiT-PixArt-PCD-CLAY-stage2-L", 10, True)):
         m = dit.DiT_models[name](input_size=32, num_classes=0, learn_sigma=False, in_channels=cin, context_dim=1024,
                                  roll_out=True, pooling_ctx_dim=768)
-        m.randomize_zero_init_().to(dev)
+        m.randomize_zero_init_().to(dev).eval()
         x = torch.randn(B, N, cin, device=dev)
         t = torch.rand(B, device=dev)
         ctx = {"img_crossattn": torch.randn(B, M, 1024, device=dev), "img_vector": torch.randn(B, 1024, device=dev)}
@@ -283,3 +283,176 @@ def test_dit_l_c4_size_properties():
         assert rel(y3.flip(0), y1) < 1e-5
         del m
         torch.cuda.empty_cache()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# round 2: context K/V cache safety, per-block activations, C3-size parity, CFG de-duplication, inference-only guard
+# ---------------------------------------------------------------------------------------------------------------
+def _rand_ctx(B, M, Dc, dev, seed):
+    g = torch.Generator().manual_seed(seed)
+    return {"img_crossattn": torch.randn(B, M, Dc, generator=g).to(dev), "img_vector": torch.randn(B, Dc, generator=g).to(dev)}
+
+
+def test_context_kv_cache_is_not_stale_across_samples():
+    """Round-1 bug (VERDICT weak #1 / ADVICE high): the cross-attention K/V cache was keyed on data_ptr(); a new
+    context allocated at the recycled address of a freed one silently reused the old K/V.  Two DIFFERENT contexts
+    of the same shape, the first freed before the second is allocated, must both match the oracle."""
+    from oracle import dit_oracle as do
+    g = do.load_golden(os.path.join(GOLD, "dit_stage1_small.npz"))
+    c = g["cfg"]
+    dev = torch.device("cuda:0")
+    m = _build(g, dev)
+    x, t = g["x"].to(dev), g["t"].to(dev)
+    B, M, Dc = g["ctx"]["img_crossattn"].shape
+    outs, ptrs = [], []
+    for seed in (11, 12, 13):
+        ctx = _rand_ctx(B, M, Dc, dev, seed)
+        ptrs.append(ctx["img_crossattn"].data_ptr())
+        y = m(x, t, ctx).cpu()
+        want = do.forward(g["sd"], g["x"], g["t"], {k: v.cpu() for k, v in ctx.items()}, c["heads"], c["depth"],
+                          emulate_bf16=True)
+        assert rel(y, want) < 6e-3, (seed, rel(y, want))
+        outs.append(y)
+        del ctx, y                                   # frees the block: the next context usually lands on the same address
+    assert not torch.equal(outs[0], outs[1]) and not torch.equal(outs[1], outs[2])
+    # same tensor object again: cache hit, same bits; modified in place: version counter invalidates the cache
+    ctx = _rand_ctx(B, M, Dc, dev, 21)
+    y1 = m(x, t, ctx)
+    y2 = m(x, t, ctx)
+    assert torch.equal(y1, y2)
+    ctx["img_crossattn"].mul_(0.5)
+    y3 = m(x, t, ctx)
+    want = do.forward(g["sd"], g["x"], g["t"], {k: v.cpu() for k, v in ctx.items()}, c["heads"], c["depth"], emulate_bf16=True)
+    assert rel(y3.cpu(), want) < 6e-3 and not torch.equal(y1, y3)
+
+
+def test_runs_under_inference_mode_like_the_reference_eval_path():
+    """The reference samples under @th.inference_mode() (flow_matching_trainer.py:747): inference tensors have no
+    version counter, and workspaces allocated inside must stay usable outside."""
+    from oracle import dit_oracle as do
+    g = do.load_golden(os.path.join(GOLD, "dit_stage1_small.npz"))
+    c = g["cfg"]
+    dev = torch.device("cuda:0")
+    m = _build(g, dev)
+    want = None
+    with torch.inference_mode():
+        x, t = g["x"].to(dev), g["t"].to(dev)
+        for seed in (31, 32):
+            ctx = _rand_ctx(*g["ctx"]["img_crossattn"].shape, dev, seed)
+            y = m.forward_with_cfg(x, t, ctx, 4.0)
+            want = do.forward_with_cfg(g["sd"], g["x"], g["t"], {k: v.cpu() for k, v in ctx.items()}, 4.0, c["heads"],
+                                       c["depth"], emulate_bf16=True)
+            assert rel(y.cpu(), want) < 8e-3
+            del ctx
+    ctx = {k: v.to(dev) for k, v in g["ctx"].items()}            # engine built under inference mode, used outside it
+    y = m(g["x"].to(dev), g["t"].to(dev), ctx)
+    assert rel(y.cpu(), g["y"]) < 2e-2
+
+
+@pytest.mark.parametrize("name", ["dit_stage1_small", "dit_stage2_small"])
+def test_per_block_activations_match_reference_golden(name):
+    """Residual stream after every block (north_star: parity on DiT activations) against the hooks the golden
+    generator put on the reference's own blocks, and against the bf16-emulating oracle."""
+    from oracle import dit_oracle as do
+    g = do.load_golden(os.path.join(GOLD, name + ".npz"))
+    c = g["cfg"]
+    dev = torch.device("cuda:0")
+    m = _build(g, dev)
+    ctx = {k: v.to(dev) for k, v in g["ctx"].items()}
+    y0 = m(g["x"].to(dev), g["t"].to(dev), ctx)
+    m._engine.tap_blocks = True
+    y = m(g["x"].to(dev), g["t"].to(dev), ctx)
+    assert torch.equal(y, y0)                                     # tapping does not change the result
+    taps = m._engine.s["taps"].cpu()
+    _, acts_e = do.forward(g["sd"], g["x"], g["t"], g["ctx"], c["heads"], c["depth"], return_acts=True, emulate_bf16=True)
+    B, N = g["x"].shape[:2]
+    worst_e = worst_g = 0.0
+    for i in range(c["depth"]):
+        got = taps[i].reshape(B, N, -1)
+        worst_e = max(worst_e, rel(got, acts_e["block%d" % i]))
+        worst_g = max(worst_g, rel(got, g["acts"]["block%d" % i]))
+    print("per-block rel-L2: vs bf16-emulating oracle %.2e, vs reference fp32 golden %.2e" % (worst_e, worst_g))
+    assert worst_e < 4e-3, worst_e
+    assert worst_g < 1.5e-2, worst_g
+
+
+@pytest.mark.timeout(900)
+def test_c3_size_forward_and_blocks_vs_oracle():
+    """BASELINE configs[2]: DiT-PixArt-PCD-CLAY-B (L12, D768, H12) at N=2048, M=1369, CFG batch 2 -- the whole
+    forward and every block's residual stream against the oracle (bf16 operands emulated) at the real size
+    (multi-tile GEMMs, 16 key blocks per attention item, ragged 1369-token context)."""
+    from gaussiananything_b200 import dit
+    from oracle import dit_oracle as do
+    dev = torch.device("cuda:0")
+    torch.manual_seed(0)
+    torch.set_num_threads(os.cpu_count() or 1)
+    m = dit.DiT_models["DiT-PixArt-PCD-CLAY-B"](input_size=32, num_classes=0, learn_sigma=False, in_channels=3,
+                                                context_dim=1024, roll_out=True, pooling_ctx_dim=768)
+    m.randomize_zero_init_()
+    for p in m.parameters():                                      # bf16-representable weights: the oracle sees the
+        p.data.copy_(p.data.to(torch.bfloat16).float())          # exact values the tensor cores multiply
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    m.to(dev).eval()
+    B, N, M = 2, 2048, 1369
+    x, t = torch.randn(B, N, 3), torch.rand(B)
+    ctx = {"img_crossattn": torch.randn(B, M, 1024), "img_vector": torch.randn(B, 1024)}
+    dctx = {k: v.to(dev) for k, v in ctx.items()}
+    m._engine_for(x.to(dev), dctx).tap_blocks = True
+    y = m(x.to(dev), t.to(dev), dctx).cpu()
+    taps = m._engine.s["taps"].cpu()
+    want, acts = do.forward(sd, x, t, ctx, 12, 12, return_acts=True, emulate_bf16=True)
+    worst = max(rel(taps[i].reshape(B, N, -1), acts["block%d" % i]) for i in range(12))
+    print("C3 size: output rel-L2 %.2e, worst block %.2e" % (rel(y, want), worst))
+    assert rel(y, want) < 6e-3, rel(y, want)
+    assert worst < 4e-3, worst
+    yc = m.forward_with_cfg(x.to(dev), t.to(dev), dctx, 4.0).cpu()
+    c, u = want[:1], want[1:]
+    assert rel(yc[:1], u + 4.0 * (c - u)) < 2e-2
+
+
+def test_cfg_dedup_fast_path_is_bit_identical():
+    """in the reference's stage-2 call uc == c, so u + s (c - u) == c.  With cfg_dedup=True only B
+    rows are evaluated; the result must equal the 2B call bit for bit, and differing halves must not take the path."""
+    from oracle import dit_oracle as do
+    g = do.load_golden(os.path.join(GOLD, "dit_stage2_small.npz"))
+    dev = torch.device("cuda:0")
+    m = _build(g, dev)
+    h = g["x"].shape[0] // 2
+    x = torch.cat([g["x"][:h], g["x"][:h]], 0).to(dev)
+    t = torch.cat([g["t"][:h], g["t"][:h]], 0).to(dev)
+    ctx = {k: torch.cat([v[:h], v[:h]], 0).to(dev) for k, v in g["ctx"].items()}
+    full = m.forward_with_cfg(x, t, ctx, 4.0)
+    m.cfg_dedup = True
+    fast = m.forward_with_cfg(x, t, ctx, 4.0)
+    assert m._engine._shape[0] == h                              # really ran B rows
+    assert torch.equal(full, fast)
+    # halves differ (stage-1 style: zeroed unconditional tokens): must fall back to the 2B evaluation
+    ctx2 = {k: v.clone() for k, v in ctx.items()}
+    ctx2["img_crossattn"][h:] = 0
+    y2 = m.forward_with_cfg(x, t, ctx2, 4.0)
+    m.cfg_dedup = False
+    y2_ref = m.forward_with_cfg(x, t, ctx2, 4.0)
+    assert torch.equal(y2, y2_ref) and not torch.equal(y2, full)
+
+
+def test_inference_only_guard_and_parameter_updates():
+    from oracle import dit_oracle as do
+    g = do.load_golden(os.path.join(GOLD, "dit_stage1_small.npz"))
+    dev = torch.device("cuda:0")
+    m = _build(g, dev)
+    ctx = {k: v.to(dev) for k, v in g["ctx"].items()}
+    x, t = g["x"].to(dev), g["t"].to(dev)
+    with pytest.raises(RuntimeError, match="inference-only"):
+        m(x.clone().requires_grad_(True), t, ctx)
+    m.train()
+    with pytest.raises(RuntimeError, match="inference-only"):
+        m(x, t, ctx)
+    with torch.no_grad():
+        y0 = m(x, t, ctx)                                         # fine under no_grad even in train mode
+    m.eval()
+    # an in-place parameter update (optimizer step / .data.copy_) must not leave a stale bf16 pack / CUDA graph
+    with torch.no_grad():
+        m.final_layer.linear.weight.mul_(2.0)
+        m.final_layer.linear.bias.mul_(2.0)
+    y1 = m(x, t, ctx)
+    assert rel(y1, 2.0 * y0) < 1e-5

@@ -305,3 +305,190 @@ def test_fused_postprocess_matches_reference_formulas_and_autograd():
     ga_ref[:, :, 5][~fin] = 0.0                      # torch propagates a gradient through nan_to_num; the value is unused
     g_allmap[:, :, 5][~fin] = 0.0
     assert torch.allclose(g_allmap, ga_ref, atol=1e-4, rtol=1e-4)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# round 2: the reference's own loop as golden, the B3 adapter, C2-size backward, the two switchable judgement calls
+# ---------------------------------------------------------------------------------------------------------------
+def test_reference_loop_golden():
+    """GaussianRenderer2DGS.render (one batched launch set) == the UNMODIFIED /root/reference/nsr/gs_surfel.py
+    B x V loop + post-processing, run on CPU over an oracle-backed diff_surfel_rasterization
+    (tests/golden/make_gs_surfel_golden.py wrote the fixture)."""
+    import os
+    from gaussiananything_b200.gs_surfel import GaussianRenderer2DGS
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "gs_surfel_loop.npz"))
+    dev = torch.device("cuda:0")
+    T = lambda a: torch.tensor(a, device=dev)
+    r = GaussianRenderer2DGS(64, 3, {"z_near": 0.01})
+    tf = float(z["tanfov"])
+    a = r.render(T(z["g"]), T(z["view"]), T(z["proj"]), T(z["pos"]), tf)
+    b = r.render(T(z["g"][:1]), T(z["view"][:1, :2]), T(z["proj"][:1, :2]), T(z["pos"][:1, :2]), tf,
+                 bg_color=T(z["b__bg"]), scale_modifier=1.6, output_size=48)
+    for tag, out in (("a", a), ("b", b)):
+        assert set(out) == {"image", "alpha", "depth", "rend_normal", "dist"}
+        for k, v in out.items():
+            want = z["%s__%s" % (tag, k)]
+            got = v.cpu().numpy()
+            assert got.shape == want.shape, (tag, k, got.shape, want.shape)
+            if k == "depth":        # median depth: a pixel whose T crosses 0.5 within rounding picks another surfel
+                bad = np.abs(got - want) > 1e-4 * np.maximum(1.0, np.abs(want))
+                assert bad.mean() <= 2e-4, (tag, k, bad.mean())
+            elif k == "dist":
+                assert rel_l2(got, want) <= TOL or np.abs(got - want).max() <= 2e-5, (tag, k)
+            else:
+                assert rel_l2(got, want) <= TOL, (tag, k, rel_l2(got, want))
+
+
+def test_gaussian_renderer_render_adapter():
+    """Boundary B3: nsr.gaussian_renderer.render(viewpoint_camera, pc, pipe, bg_color, ...) call shape."""
+    import math
+    from types import SimpleNamespace
+    from gaussiananything_b200.gaussian_renderer import render
+    P, H = 2500, 112
+    g = scene(P, 33, 6.0)
+    vs, ps, cs, tf = cameras(1, start=3)
+    dev = torch.device("cuda:0")
+    gt = torch.tensor(g, device=dev)
+    fov = 2.0 * math.atan(tf)
+    cam = SimpleNamespace(FoVx=fov, FoVy=fov, image_height=H, image_width=H,
+                          world_view_transform=torch.tensor(vs[0], device=dev),
+                          full_proj_transform=torch.tensor(ps[0], device=dev),
+                          camera_center=torch.tensor(cs[0], device=dev))
+    pc = SimpleNamespace(get_xyz=gt[:, 0:3], get_opacity=gt[:, 3:4], get_scaling=gt[:, 4:6], get_rotation=gt[:, 6:10],
+                         get_features=gt[:, 10:13], active_sh_degree=0)
+    bg = torch.tensor([0.1, 0.2, 0.3], device=dev)
+    out = render(cam, pc, SimpleNamespace(debug=False), bg, scaling_modifier=1.3)
+    assert {"render", "viewspace_points", "visibility_filter", "radii"} <= set(out)
+    o = oracle_view(g, vs[0], ps[0], [0.1, 0.2, 0.3], H, H, scale_modifier=1.3)
+    assert rel_l2(out["render"].cpu().numpy(), o["color"]) <= TOL
+    assert np.array_equal(out["radii"].cpu().numpy(), o["radii"])
+    assert np.array_equal(out["visibility_filter"].cpu().numpy(), o["radii"] > 0)
+    out2 = render(cam, pc, SimpleNamespace(debug=False), bg, override_color=torch.flip(gt[:, 10:13], dims=[1]))
+    o2 = so_rasterize_colors(g, np.ascontiguousarray(g[:, 10:13][:, ::-1]), vs[0], ps[0], [0.1, 0.2, 0.3], H)
+    assert rel_l2(out2["render"].cpu().numpy(), o2["color"]) <= TOL
+
+
+def so_rasterize_colors(g, colors, view, proj, bg, H):
+    from oracle import surfel_oracle as so
+    return so.rasterize(g[:, 0:3], g[:, 3:4], g[:, 4:6], g[:, 6:10], colors, view, proj, bg, H, H, 1.0)
+
+
+def _oracle_grad_sum(g, vs, ps, bg, H, W, gc, ga, views):
+    from oracle import surfel_oracle as so
+    P = g.shape[0]
+    want = np.zeros((P, 13))
+    for v in views:
+        o = oracle_view(g, vs[v], ps[v], bg, H, W)
+        b = so.rasterize_backward(o, gc[v], ga[v])
+        want[:, 0:3] += b["means3D"]; want[:, 3:4] += b["opacities"]; want[:, 4:6] += b["scales"]
+        want[:, 6:10] += b["rotations"]; want[:, 10:13] += b["colors"]
+    return want
+
+
+GRAD_COLS = [("means3D", slice(0, 3)), ("opacity", slice(3, 4)), ("scales", slice(4, 6)),
+             ("rotations", slice(6, 10)), ("colors", slice(10, 13))]
+
+
+def test_c2_size_backward_vs_oracle():
+    """BASELINE configs[1] (100k surfels, 512^2, 6 views): the gradient of the headline workload against the oracle --
+    one view alone, and the batched launch's sum over all 6 views."""
+    from gaussiananything_b200 import raster
+    from oracle import surfel_oracle as so
+    import os
+    so.set_num_threads(os.cpu_count() or 1)
+    P, H, W, V = 100000, 512, 512, 6
+    g = scene(P, 40)
+    vs, ps, _, _ = cameras(V)
+    bg = [1.0, 1.0, 1.0]
+    dev = torch.device("cuda:0")
+    rng = np.random.default_rng(5)
+    gc = rng.standard_normal((V, 3, H, W)).astype(np.float32)
+    ga = rng.standard_normal((V, 7, H, W)).astype(np.float32)
+    g13 = torch.tensor(g, device=dev)[None]
+    bgt = torch.tensor(bg, device=dev)
+    # one view
+    c, a, r, st = raster.forward_raw(g13, torch.tensor(vs[3:4], device=dev)[None], torch.tensor(ps[3:4], device=dev)[None],
+                                     bgt, H, W)
+    got1 = raster.backward_raw(st, torch.tensor(gc[3:4], device=dev)[None], torch.tensor(ga[3:4], device=dev)[None])
+    want1 = _oracle_grad_sum(g, vs, ps, bg, H, W, gc, ga, [3])
+    for name, sl in GRAD_COLS:
+        assert rel_l2(got1[0].cpu().numpy()[:, sl], want1[:, sl]) <= TOL, ("1 view", name)
+    # all 6 views in one launch set: gradient summed over the views
+    c, a, r, st = raster.forward_raw(g13, torch.tensor(vs, device=dev)[None], torch.tensor(ps, device=dev)[None], bgt, H, W)
+    got6 = raster.backward_raw(st, torch.tensor(gc, device=dev)[None], torch.tensor(ga, device=dev)[None])
+    want6 = _oracle_grad_sum(g, vs, ps, bg, H, W, gc, ga, range(V))
+    for name, sl in GRAD_COLS:
+        assert rel_l2(got6[0].cpu().numpy()[:, sl], want6[:, sl]) <= TOL, ("6 views", name)
+
+
+@pytest.mark.parametrize("radius_formula,quat_norm_grad", [(1, 0), (0, 1), (1, 1)])
+def test_switchable_judgement_calls(radius_formula, quat_norm_grad):
+    """The two unpinned choices of the restatement (radius formula; quaternion-normalisation gradient) are run-time
+    switches in the CUDA path and in the oracle: every combination stays in parity (integers bit-exact), and the
+    alternatives really differ from the default."""
+    import ctypes as C
+    from gaussiananything_b200 import _lib, raster
+    from oracle import surfel_oracle as so
+    lib = _lib.lib()
+    lib.ga_raster_set_variant.argtypes = [C.c_int, C.c_int]
+    P, H, W = 3000, 96, 112
+    g = scene(P, 50, 6.0)
+    g[:, 6:10] *= np.linspace(0.5, 2.0, P, dtype=np.float32)[:, None]        # non-unit quaternions
+    vs, ps, _, _ = cameras(1, start=2)
+    bg = [0.3, 0.6, 0.9]
+    dev = torch.device("cuda:0")
+    rng = np.random.default_rng(1)
+    gc = rng.standard_normal((1, 3, H, W)).astype(np.float32)
+    ga = rng.standard_normal((1, 7, H, W)).astype(np.float32)
+
+    def run():
+        g13 = torch.tensor(g, device=dev)[None]
+        c, a, r, st = raster.forward_raw(g13, torch.tensor(vs, device=dev)[None], torch.tensor(ps, device=dev)[None],
+                                         torch.tensor(bg, device=dev), H, W)
+        grad = raster.backward_raw(st, torch.tensor(gc, device=dev)[None], torch.tensor(ga, device=dev)[None])
+        wsv = raster.workspace_views(st["ws"], st["L"], 1, P, 1, H, W, st["max_instances"])
+        return c, a, r, st, wsv, grad[0].cpu().numpy()
+
+    base = run()
+    try:
+        lib.ga_raster_set_variant(radius_formula, quat_norm_grad)
+        so.set_variant(radius_formula, quat_norm_grad)
+        c, a, r, st, wsv, grad = run()
+        o = oracle_view(g, vs[0], ps[0], bg, H, W)
+        assert st["num_rendered"] == o["num_rendered"]
+        _check_view(o, c[0, 0], a[0, 0], r[0, 0], wsv, 0, P, H, W)
+        want = _oracle_grad_sum(g, vs, ps, bg, H, W, gc, ga, [0])
+        for name, sl in GRAD_COLS:
+            assert rel_l2(grad[:, sl], want[:, sl]) <= TOL, name
+        if radius_formula:
+            assert (r[0, 0] >= base[2][0, 0]).all() and (r[0, 0] > base[2][0, 0]).any()
+            assert rel_l2(c.cpu().numpy(), base[0].cpu().numpy()) <= 1e-3       # larger tile lists, same pixels
+        else:
+            assert torch.equal(r, base[2])
+        if quat_norm_grad:
+            assert rel_l2(grad[:, 6:10], base[5][:, 6:10]) > 1e-2
+            q = g[:, 6:10].astype(np.float64)
+            assert np.abs((grad[:, 6:10] * q).sum(1)).max() <= 1e-3 * np.abs(grad[:, 6:10]).max() * 4   # radial part removed
+    finally:
+        lib.ga_raster_set_variant(0, 0)
+        so.set_variant(0, 0)
+
+
+def test_render_sharded_world1_matches_manual_loop():
+    """sharding.render_sharded on one rank (no process group) == rendering every (sample, view) pair by hand."""
+    from gaussiananything_b200 import sharding
+    from gaussiananything_b200.gs_surfel import GaussianRenderer2DGS
+    dev = torch.device("cuda:0")
+    S, V, P, H = 2, 3, 1500, 64
+    g = torch.tensor(np.stack([scene(P, 60, 8.0), scene(P, 61, 5.0)]), device=dev)
+    vs, ps, cs, tf = cameras(S * V)
+    cv = torch.tensor(vs, device=dev).reshape(S, V, 4, 4)
+    cp = torch.tensor(ps, device=dev).reshape(S, V, 4, 4)
+    pos = torch.tensor(cs, device=dev).reshape(S, V, 3)
+    r = GaussianRenderer2DGS(H, 3, {})
+    got = sharding.render_sharded(r, g, cv, cp, pos, tf)
+    assert set(got) == {(b, v) for b in range(S) for v in range(V)}
+    full = r.render(g, cv, cp, pos, tf)
+    for (b, v), d in got.items():
+        for k, t in d.items():
+            assert torch.equal(t, full[k][b, v]), (b, v, k)
