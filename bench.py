@@ -28,6 +28,9 @@ if ROOT not in sys.path:
 import numpy as np  # noqa: E402
 
 P_SURFELS, RES, VIEWS = 100000, 512, 6
+# kernels of libga_b200.so per device-timed step: preprocess, tile scan, scatter, 2 sort kernels, render fwd | render bwd,
+# preprocess bwd (+ 3 memsets, not counted)
+LAUNCHES_PER_STEP = 8
 METRIC = "512^2 views/sec @100k Gaussians (surfel raster fwd+bwd)"
 UNIT = "views/s"
 CONFIG = {"workload": "C2: 100k surfels, 512x512, 6 views, raster fwd+bwd",
@@ -45,11 +48,35 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def make_inputs(seed):
+def make_inputs(seed, P=P_SURFELS, views=VIEWS):
+    """Seeded synthetic scene + look-at cameras (tools/synth.py: numpy only -- the GPU arm never loads the oracle)."""
     from tests.helpers import cameras, scene
-    g = scene(P_SURFELS, seed)
-    vs, ps, _, tf = cameras(VIEWS)
+    g = scene(P, seed)
+    vs, ps, _, tf = cameras(views)
     return g, vs, ps
+
+
+def pin_to_gpu_numa_node(local):
+    """Binds this process to the CPUs next to its GPU (sysfs local_cpulist of the GPU's PCI function) BEFORE any
+    pinned host buffer is allocated, so the staging memory of every rank is first-touched on its GPU's NUMA node
+    (8 ranks uploading 24 MB per step through the wrong socket was the e2e limiter at N=8 in round 1)."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(local)
+        bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        with open("/sys/bus/pci/devices/%s/local_cpulist" % bdf) as f:
+            txt = f.read().strip()
+        cpus = set()
+        for part in txt.split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return {"pci": bdf, "cpus": len(cpus)}
+    except Exception as ex:                                  # not fatal: report and carry on unpinned
+        return {"error": repr(ex)}
+    return {"cpus": 0}
 
 
 class ClockSampler:
@@ -167,6 +194,7 @@ def run_gpu(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = pin_to_gpu_numa_node(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.lib()
@@ -299,22 +327,51 @@ def run_gpu(args):
         ev_done.record()
         state["done"] = ev_done
 
-    for _ in range(3):
-        step_e2e()
-    torch.cuda.synchronize(dev)
-    barrier()
-    e0 = time.perf_counter()
-    for _ in range(args.steps):
+    # >= 20 warm-up steps, then >= 500 steps AND >= 2 s (round 1 timed 20 steps = 29 ms after 3 warm-up steps: one
+    # allocator / engine stall made BENCH and SCALE N=1 disagree 24x).  Per-step host times are kept: the mean gives
+    # the throughput, the median / p99 / max show whether a stall was inside the window.
+    for _ in range(20):
         step_e2e()
     state["done"].synchronize()
+    torch.cuda.synchronize(dev)
+    import gc
+    gc.collect()
+    gc.disable()                                                  # no collector pause inside the window
+    barrier()
+    e2e_steps, step_s = 0, []
+    e0 = time.perf_counter()
+    while e2e_steps < max(args.steps, 500) or (time.perf_counter() - e0) < 2.0:
+        t_a = time.perf_counter()
+        step_e2e()
+        step_s.append(time.perf_counter() - t_a)
+        e2e_steps += 1
+        if e2e_steps >= 20000:
+            break
+    state["done"].synchronize()
+    e_local = time.perf_counter() - e0
+    gc.enable()
     assert bool(torch.isfinite(h_loss).all()) and bool(torch.isfinite(h_grad).all())
     barrier()
-    e_wall = time.perf_counter() - e0
-    t = torch.tensor([e_wall], device=dev, dtype=torch.float64)
+    # every rank ran for >= 2 s but not the same number of steps: whole-job rate = sum of the per-rank rates
+    t = torch.tensor([V * e2e_steps / e_local], device=dev, dtype=torch.float64)
     if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * V * args.steps / float(t.item())
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    e2e_value = float(t.item())
+    step_s = np.array(step_s)
+    e2e_stats = {"steps": e2e_steps, "seconds": e_local, "warmup_steps": 20,
+                 "ms_per_step_mean": 1e3 * e_local / e2e_steps, "ms_per_step_median": 1e3 * float(np.median(step_s)),
+                 "ms_per_step_p99": 1e3 * float(np.percentile(step_s, 99)), "ms_per_step_max": 1e3 * float(step_s.max()),
+                 "steps_over_5x_median": int((step_s > 5 * np.median(step_s)).sum()),
+                 "value_from_median": V / float(np.median(step_s)), "numa_pinning": numa}
 
+    c5 = None
+    if not args.no_c5:
+        try:
+            c5 = run_c5_leg(dev, world, rank, with_cascade=not args.no_dit)
+        except Exception as ex:
+            if world > 1:
+                raise                                  # a collective leg that half the ranks abandon would hang the job
+            c5 = {"error": repr(ex)}
     if rank == 0:
         hbm, peak_src = measured_peaks()
         HW = H * W
@@ -355,10 +412,23 @@ def run_gpu(args):
                     dit_leg["vae_decoder_N1"] = {"error": repr(ex)}
             except Exception as ex:                      # the raster metric is the headline; report, do not hide
                 dit_leg = {"error": repr(ex)}
+        standin = None
+        if world == 1 and not args.no_dit:
+            try:
+                standin = run_gpu_standin(dev)
+                if isinstance(dit_leg, dict) and "ms_per_nfe" in dit_leg:
+                    a = standin["dit_C3_B_N2048"]
+                    best = min(v for k, v in a.items() if k.endswith("ms_per_nfe"))
+                    standin["speedup_C3_vs_best_standin"] = best / dit_leg["ms_per_nfe"]
+                    b = standin["dit_deployed_L_N768"]
+                    best = min(v for k, v in b.items() if k.endswith("ms_per_nfe"))
+                    standin["speedup_deployed_L_vs_best_standin"] = best / dit_leg["deployed_L_N768"]["DiT-PixArt-PCD-CLAY-L"]["ms_per_nfe"]
+            except Exception as ex:
+                standin = {"error": repr(ex)}
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                "warmup": max(args.warmup, 3), "ms_per_step": dev_ms_max / args.steps,
                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-               "data": "synthetic", "config": dict(CONFIG, instances_D=D),
+               "data": "synthetic", "config": CONFIG, "instances_D": D,
                "wall_s_timed_region": wall, "stage_ms": stages,
                "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": hbm, "unit": "GB/s",
                             "frac": achieved / hbm, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
@@ -368,8 +438,10 @@ def run_gpu(args):
                                  "sample": "%d views fwd+bwd of the same 100k/512^2 scene in %.1f s "
                                            "(oracle/surfel_oracle.c, OpenMP)" % (cpu_n, cpu_dt)}
                                 if world == 1 else None),
-               "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-               "gpu_launches": 8 * args.steps, "clocks": clocks, "dit": dit_leg}
+               "e2e": dict({"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+                           **e2e_stats),
+               "gpu_launches": LAUNCHES_PER_STEP * args.steps, "clocks": clocks, "dit": dit_leg, "c5": c5,
+               "gpu_standin": standin}
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
@@ -531,13 +603,162 @@ def run_dit_deployed_leg(dev, nfe=20, N=768):
     return out
 
 
+# ---------------------------------------------------------------------------
+# C5 leg (BASELINE.json configs[4]): the cascade's multi-GPU data path, one sample per rank:
+#   [DiT-L stage 1 -> stage 2 sampling] -> VAE decode (73 728 surfels) -> ONE NCCL all-gather of the decoded
+#   surfels -> every rank renders its interleaved share of all (sample, view) pairs (8 views of 512^2 per sample).
+# Reference hand-off being replaced: nsr/lsgm/flow_matching_trainer.py:1399-1424,1545-1567 (decode once, then a
+# per-camera render loop on one GPU; scripts/gradio_app_cascaded.py:96-100 pins world size 1).
+# ---------------------------------------------------------------------------
+C5_VIEWS, C5_RES, C5_TOKENS = 8, 512, 768
+
+
+def run_c5_leg(dev, world, rank, steps=20, cascade_samples=2, with_cascade=True):
+    import torch
+    import torch.distributed as dist
+    from gaussiananything_b200 import dit, sharding, transport as tr
+    from gaussiananything_b200.gs_surfel import GaussianRenderer2DGS
+    from gaussiananything_b200.vae_decoder import SurfelDecoder, random_state_dict
+    from tests.helpers import cameras
+    torch.manual_seed(100 + rank)
+    dec = SurfelDecoder(random_state_dict(768, 12, 10, seed=0), 12, 12, device=dev)
+    rnd = GaussianRenderer2DGS(C5_RES, 3, {})
+    S, V = world, C5_VIEWS
+    vs, ps, cs, tf = cameras(S * V)
+    cv = torch.tensor(vs, device=dev).reshape(S, V, 4, 4)
+    cp = torch.tensor(ps, device=dev).reshape(S, V, 4, 4)
+    pos = torch.tensor(cs, device=dev).reshape(S, V, 3)
+    lat = torch.randn(1, C5_TOKENS, 10, device=dev)
+    xyz = (torch.rand(1, C5_TOKENS, 3, device=dev) - 0.5) * 0.8
+
+    def sync_max(x):
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+
+    def decode_gather_render(latent, points):
+        e = [ev() for _ in range(4)]
+        e[0].record()
+        surf = dec.decode(latent, points)["gaussians_upsampled_3"]            # [1, 73728, 13], the all-gather send buffer
+        e[1].record()
+        allg = sharding.all_gather_surfels(surf)                               # the path's only collective
+        e[2].record()
+        out = _render_owned(allg)
+        e[3].record()
+        return e, out, surf
+
+    def _render_owned(allg):
+        # surfels are already gathered: render this rank's pairs (render_sharded's body after its all-gather)
+        by = sharding.group_pairs_by_sample(sharding.shard_pairs(S, V, world, rank))
+        samples = list(by)
+        nv = {len(v) for v in by.values()}
+        assert len(nv) == 1
+        bi = torch.tensor(samples, device=dev)
+        vi = torch.tensor([by[b] for b in samples], device=dev)
+        rows = bi[:, None].expand(-1, vi.shape[1])
+        return rnd.render(allg[bi], cv[rows, vi], cp[rows, vi], pos[rows, vi], tf)
+
+    with torch.no_grad():
+        for _ in range(3):
+            decode_gather_render(lat, xyz)
+        barrier()
+        recs = []
+        w0 = ev(); w1 = ev()
+        w0.record()
+        for _ in range(steps):
+            recs.append(decode_gather_render(lat, xyz)[0])
+        w1.record()
+        w1.synchronize()
+        barrier()
+    total_ms = sync_max(w0.elapsed_time(w1))
+    dec_ms = float(np.mean([r[0].elapsed_time(r[1]) for r in recs]))
+    ag_ms = float(np.mean([r[1].elapsed_time(r[2]) for r in recs]))
+    ren_ms = float(np.mean([r[2].elapsed_time(r[3]) for r in recs]))
+    P = 73728
+    out = {"config": "C5 data path: per rank 1 sample: VAE decode (768 tokens -> 73728 surfels) -> NCCL all-gather of "
+                     "[1,73728,13] f32 per rank -> render this rank's share of %d samples x %d views of %d^2 (forward)"
+                     % (S, V, C5_RES),
+           "n_gpus": world, "steps": steps, "views_per_step": S * V,
+           "views_per_s": S * V * steps / (total_ms * 1e-3), "samples_per_s_decode_gather_render": S * steps / (total_ms * 1e-3),
+           "ms_per_step": total_ms / steps,
+           "stage_ms_rank0": {"vae_decode": dec_ms, "all_gather": ag_ms, "render_shard": ren_ms},
+           "collective": {"op": "ncclAllGather (torch.distributed all_gather_into_tensor)" if world > 1 else "none (world 1)",
+                          "bytes_per_rank": P * 13 * 4, "bytes_total": world * P * 13 * 4,
+                          "us_max_over_ranks": 1e3 * sync_max(ag_ms),
+                          "algbw_GBs": (world * P * 13 * 4 / 1e9) / (ag_ms * 1e-3) if world > 1 and ag_ms > 0 else None}}
+    if with_cascade:
+        # the whole cascade per sample (minus the DINOv2 conditioner, row N3): 2 x 249 Euler NFE with CFG on random-init
+        # DiT-L weights at the deployed N = 768, then decode / gather / render as above
+        M, Dc = 1369, 1024
+        mk = lambda name, cin: dit.DiT_models[name](input_size=32, num_classes=0, learn_sigma=False, in_channels=cin,
+                                                    context_dim=Dc, roll_out=True, pooling_ctx_dim=768).randomize_zero_init_().to(dev).eval()
+        m1, m2 = mk("DiT-PixArt-PCD-CLAY-L", 3), mk("DiT-PixArt-PCD-CLAY-stage2-L", 10)
+        sampler = tr.Sampler(tr.create_transport("GVP", "velocity", None, None, None, "lognorm"))
+        fn = sampler.sample_ode(sampling_method="euler", num_steps=250)
+        h_ctx, h_vec = torch.randn(1, M, Dc).pin_memory(), torch.randn(1, Dc).pin_memory()
+
+        def one_sample(dedup):
+            c, v = h_ctx.to(dev, non_blocking=True), h_vec.to(dev, non_blocking=True)
+            ctx1 = {"img_crossattn": torch.cat([c, torch.zeros_like(c)], 0), "img_vector": torch.cat([v, torch.zeros_like(v)], 0)}
+            z = torch.randn(1, C5_TOKENS, 3, device=dev)
+            pts = fn(torch.cat([z, z], 0), m1.forward_with_cfg, context=ctx1, cfg_scale=4.0)[-1][:1]
+            pts = (pts * 0.164).clamp(-0.45, 0.45)                               # stage-1 un-normalisation (flow_matching_trainer.py:987)
+            fps = torch.cat([pts, pts], 0) / 0.45
+            ctx2 = {"img_crossattn": torch.cat([c, c], 0), "img_vector": torch.cat([v, v], 0), "fps-xyz": fps}   # uc == c
+            m2.cfg_dedup = dedup
+            z2 = torch.randn(1, C5_TOKENS, 10, device=dev)
+            latent = fn(torch.cat([z2, z2], 0), m2.forward_with_cfg, context=ctx2, cfg_scale=4.0)[-1][:1]
+            e, o, surf = decode_gather_render(latent, pts)
+            return o
+
+        res = {}
+        with torch.no_grad():
+            for tag, dedup in (("reference_cfg_2B_both_stages", False), ("stage2_cfg_dedup_opt_in", True)):
+                one_sample(dedup)                                                # warm-up: packs, K/V, graphs
+                barrier()
+                t0 = time.perf_counter()
+                for _ in range(cascade_samples):
+                    o = one_sample(dedup)
+                h_img = o["image"][:, :1, :, :8, :8].cpu()                           # a device->host read ends each timed window
+                torch.cuda.synchronize(dev)
+                dt = sync_max(time.perf_counter() - t0)
+                barrier()
+                res[tag] = {"seconds_per_sample_per_gpu": dt / cascade_samples, "samples_per_s": world * cascade_samples / dt}
+        out["cascade"] = dict(res, config="DiT-PixArt-PCD-CLAY-L + ...-stage2-L (L24 D1024 H16), N=768, M=1369, 250-point Euler "
+                              "grids (2 x 249 NFE), CFG 4.0, bf16 -> VAE decode -> all-gather -> %d views of %d^2; no DINOv2 "
+                              "conditioner (SURVEY 8f N3 not built): context tokens are synthetic" % (V, C5_RES),
+                              samples_per_step=world)
+        del m1, m2
+        torch.cuda.empty_cache()
+    return out
+
+
+def run_gpu_standin(dev):
+    """GPU comparison baselines on the same B200 (baseline/gpu_standin.py)."""
+    from baseline import gpu_standin as gs
+    out = {"what": "unfused PyTorch-CUDA restatement of the reference's DiT block stack: nn.Linear under bf16 autocast (cuBLAS) + "
+                   "flash_attn_func + separate norm/modulate/GELU kernels, context K/V re-projected every block, 2B CFG forward"}
+    out["dit_C3_B_N2048"] = gs.time_torch_dit(dev, 12, 768, 12, 2048, nfe=20)
+    out["dit_deployed_L_N768"] = gs.time_torch_dit(dev, 24, 1024, 16, 768, nfe=20)
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--no-dit", action="store_true", help="skip the secondary DiT sampling leg")
+    ap.add_argument("--no-dit", action="store_true", help="skip the secondary DiT sampling legs (DiT, cascade, stand-ins)")
+    ap.add_argument("--no-c5", action="store_true", help="skip the C5 decode -> all-gather -> render leg")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

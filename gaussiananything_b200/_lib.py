@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libga_b200.so")
+# GA_B200_LIB: load a tuning build (gaussiananything_b200/build.py --variant) instead of the product library
+LIB_PATH = os.environ.get("GA_B200_LIB") or os.path.join(_HERE, "libga_b200.so")
 
 _lib = None
 

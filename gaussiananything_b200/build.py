@@ -34,8 +34,12 @@ def sources():
     return sorted(f for f in os.listdir(CSRC) if f.endswith(".cu"))
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, variant: str = "", extra_flags=()) -> str:
+    """variant != "": a tuning build libga_b200_<variant>.so with `extra_flags` (e.g. -DBWD_CTAS=3) in its own object
+    directory; load it with GA_B200_LIB=<path> (gaussiananything_b200/_lib.py).  The default build is the product."""
     nvcc = _nvcc()
+    OUT = os.path.join(HERE, "libga_b200%s.so" % (("_" + variant) if variant else ""))
+    OBJ = os.path.join(HERE, "csrc", "_obj" + (("_" + variant) if variant else ""))
     os.makedirs(OBJ, exist_ok=True)
     hdrs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
     hdrs.append(os.path.join(HERE, "..", "include", "ga_b200.h"))
@@ -49,7 +53,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
                 and os.path.getmtime(obj) >= max(os.path.getmtime(src), hdr_m)):
             continue
         # GA_B200_NVCC_EXTRA="-DFOO=1 ...": extra flags for every file (tuning experiments; use with --force)
-        cmd = [nvcc] + ARCH + COMMON + EXTRA.get(f, []) + os.environ.get("GA_B200_NVCC_EXTRA", "").split() + ["-c", src, "-o", obj]
+        cmd = [nvcc] + ARCH + COMMON + EXTRA.get(f, []) + os.environ.get("GA_B200_NVCC_EXTRA", "").split() + list(extra_flags) + ["-c", src, "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         r = subprocess.run(cmd, capture_output=True, text=True)
@@ -67,4 +71,10 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    # python -m gaussiananything_b200.build [--force] [-v] [--variant NAME -DFLAG=1 ...]
+    var, flags = "", []
+    if "--variant" in sys.argv:
+        i = sys.argv.index("--variant")
+        var = sys.argv[i + 1]
+        flags = [a for a in sys.argv[i + 2:] if a.startswith("-D")]
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, variant=var, extra_flags=flags))

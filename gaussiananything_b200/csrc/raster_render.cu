@@ -17,6 +17,9 @@
 #include <cstdlib>
 
 #define CHUNK 256
+#ifndef GA_FWD_GROUP_DEFAULT
+#define GA_FWD_GROUP_DEFAULT 32
+#endif
 
 // single-instruction approximations (MUFU.RCP / MUFU.EX2, <= 2 ulp): the IEEE division and the range-checked
 // __expf cost ~10 instructions each in the inner loop; parity with the oracle stays ~1e-6 relative.
@@ -77,26 +80,36 @@ __device__ __forceinline__ bool eval_pair(const float4 a, const float4 b, const 
 //  f0 = C.x C.y C.z A.x | f1 = A.y A.z B.x B.y | f2 = B.z Tw.x Tw.y Tw.z
 //  f3 = xy.x-o.x xy.y-o.y opacity - | f4 = cull box (tile-local x0 x1 y0 y1)
 //  f5 = n.x n.y n.z r | f6 = g b - -
-// warp-uniform surfel iteration (every lane evaluates the same surfel).  A variant in which every lane walks its own
-// stream of hits needed 40 % fewer evaluation rounds but lost them again to non-broadcast shared-memory reads
-// (0.208 vs 0.199 ms): removed, see DESIGN.md.
-__global__ void __launch_bounds__(256)
+// Lane groups.  A warp owns an 8x4 pixel block; GS = 32 evaluates one surfel per round for the whole block
+// (warp-uniform shared-memory reads).  With the C2 scene a surfel's cull box covers ~25 pixels, so only ~9 of the 32
+// lanes of a hit carry a contributing pixel.  GS = 16 splits the warp into two 4x4 blocks, GS = 8 into four 4x2
+// blocks; every group walks ITS OWN list of hits, so a round evaluates up to 32 / GS different surfels (2 or 4
+// distinct shared-memory addresses per load instead of one).  Measured on the C2 scene (tools/raster_rounds.py):
+// 33.9 rounds per warp and chunk with GS = 32, 24.6 with GS = 16, 20.1 with GS = 8 (13.5 with one list per lane, but
+// per-lane lists make every load a 32-address gather: 0.208 vs 0.199 ms in round 1).  Results do not depend on GS:
+// the per-pixel sequence of contributing surfels is the same.
+template <int GS>
+__global__ void __launch_bounds__(256, 4)
 render_fwd_kernel(RasterDims d, RasterWs ws, const float *__restrict__ bg,
                   float *__restrict__ out_color, float *__restrict__ out_allmap)
 {
+    constexpr int NG = 32 / GS;                                  // groups per warp
+    constexpr int GW = GS == 32 ? 8 : 4;                         // group block width / height in pixels
+    constexpr int GH = GS == 8 ? 2 : 4;
     __shared__ float4 s_rec[7][CHUNK];
     if (ws.status[1]) return;
     const int view = blockIdx.z;
     const int tile = blockIdx.y * d.gx + blockIdx.x;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int grp = lane / GS, gl = lane % GS;
     const int ox = blockIdx.x * GA_BLOCK_X, oy = blockIdx.y * GA_BLOCK_Y;
-    const int lx0 = (warp & 1) * 8, ly0 = (warp >> 1) * 4;       // warp's 8x4 block, tile-local
-    const int lxi = lx0 + (lane & 7), lyi = ly0 + (lane >> 3);
+    const int wx0 = (warp & 1) * 8, wy0 = (warp >> 1) * 4;       // warp's 8x4 block, tile-local
+    // group blocks tile the warp block: GS=16 -> 2 side by side (4x4); GS=8 -> 2x2 arrangement of 4x2 blocks
+    const int lx0 = wx0 + (GS == 32 ? 0 : (grp & 1) * 4), ly0 = wy0 + (GS == 8 ? (grp >> 1) * 2 : 0);
+    const int lxi = lx0 + (gl % GW), lyi = ly0 + (gl / GW);
     const int pxi = ox + lxi, pyi = oy + lyi;
     const bool inside = pxi < d.W && pyi < d.H;
     const float dxf = (float)lxi, dyf = (float)lyi;
-    const float bx_lo = (float)lx0, bx_hi = (float)(lx0 + 7);
-    const float by_lo = (float)ly0, by_hi = (float)(ly0 + 3);
     const float oxf = (float)ox, oyf = (float)oy;
 
     const uint32_t start = ws.tile_start[(size_t)view * d.T + tile];
@@ -135,14 +148,22 @@ render_fwd_kernel(RasterDims d, RasterWs ws, const float *__restrict__ bg,
         for (int g0 = 0; g0 < cnt; g0 += 32) {
             if (__all_sync(0xffffffffu, done)) break;
             const int j = g0 + lane;
-            bool hit = false;
-            if (j < cnt) {
-                const float4 bb = s_rec[4][j];
-                hit = !(bb.y < bx_lo || bb.x > bx_hi || bb.w < by_lo || bb.z > by_hi);
+            // lane tests surfel j against the block of every group of the warp; each lane keeps its group's ballot
+            unsigned mask = 0;
+            {
+                float4 bb = make_float4(1e30f, -1e30f, 1e30f, -1e30f);
+                if (j < cnt) bb = s_rec[4][j];
+#pragma unroll
+                for (int q = 0; q < NG; q++) {
+                    const float qx0 = (float)(wx0 + (GS == 32 ? 0 : (q & 1) * 4)), qy0 = (float)(wy0 + (GS == 8 ? (q >> 1) * 2 : 0));
+                    const bool hit = !(bb.y < qx0 || bb.x > qx0 + (float)(GW - 1) || bb.w < qy0 || bb.z > qy0 + (float)(GH - 1));
+                    const unsigned m = __ballot_sync(0xffffffffu, hit);
+                    if (q == grp) mask = m;
+                }
             }
-            unsigned mask = __ballot_sync(0xffffffffu, hit);
-            while (mask) {
-                const int jj = g0 + __ffs(mask) - 1;
+            while (__any_sync(0xffffffffu, mask != 0)) {
+                const bool active = mask != 0;
+                const int jj = g0 + (active ? __ffs(mask) - 1 : 0);
                 mask &= mask - 1;
                 const float4 f0 = s_rec[0][jj], f1 = s_rec[1][jj], f2 = s_rec[2][jj], f3 = s_rec[3][jj];
                 const float p0 = f0.x + dxf * f0.w + dyf * f1.z;
@@ -157,7 +178,7 @@ render_fwd_kernel(RasterDims d, RasterWs ws, const float *__restrict__ bg,
                 const float depth = (rho3d <= rho2d) ? (s0 * f2.y + s1 * f2.z) + f2.w : f2.w;
                 // power = -0.5*rho > 0 never happens for rho >= 0; NaN rho (p2 == 0) fails the alpha test
                 const float alpha = fminf(0.99f, f3.z * fast_ex2(rho * GA_NEG_HALF_LOG2E));
-                bool ok = !done && p2 != 0.0f && depth >= GA_NEAR_N && alpha >= 1.0f / 255.0f;
+                bool ok = active && !done && p2 != 0.0f && depth >= GA_NEAR_N && alpha >= 1.0f / 255.0f;
                 float test_T = 0.f;
                 if (ok) {
                     test_T = T * (1 - alpha);
@@ -203,11 +224,27 @@ render_fwd_kernel(RasterDims d, RasterWs ws, const float *__restrict__ bg,
     }
 }
 
+// GA_B200_FWD_GROUP=32|16|8 (or ga_raster_set_tuning) selects the lane-group size; see the kernel comment
+static int g_fwd_group = -1;
+extern "C" int ga_raster_set_tuning(int fwd_group)
+{
+    if (fwd_group != 32 && fwd_group != 16 && fwd_group != 8) return -1;
+    g_fwd_group = fwd_group;
+    return 0;
+}
+
 cudaError_t ga_launch_render_fwd(const RasterDims &d, const RasterWs &w, const float *bg,
                                  float *out_color, float *out_allmap, cudaStream_t s)
 {
+    if (g_fwd_group < 0) {
+        const char *e = getenv("GA_B200_FWD_GROUP");
+        const int v = e ? atoi(e) : GA_FWD_GROUP_DEFAULT;
+        g_fwd_group = (v == 32 || v == 16 || v == 8) ? v : GA_FWD_GROUP_DEFAULT;
+    }
     dim3 grid(d.gx, d.gy, d.NV);
-    render_fwd_kernel<<<grid, 256, 0, s>>>(d, w, bg, out_color, out_allmap);
+    if (g_fwd_group == 32) render_fwd_kernel<32><<<grid, 256, 0, s>>>(d, w, bg, out_color, out_allmap);
+    else if (g_fwd_group == 16) render_fwd_kernel<16><<<grid, 256, 0, s>>>(d, w, bg, out_color, out_allmap);
+    else render_fwd_kernel<8><<<grid, 256, 0, s>>>(d, w, bg, out_color, out_allmap);
     return cudaGetLastError();
 }
 
@@ -225,13 +262,20 @@ cudaError_t ga_launch_render_fwd(const RasterDims &d, const RasterWs &w, const f
 // This replaces a 32-lane reduction per (warp, surfel) hit -- where typically 8 of 32 lanes carried data --
 // by register accumulation over the pixels a surfel actually touches.
 // ---------------------------------------------------------------------------
+#ifndef BWD_CTAS
+#define BWD_CTAS 2                  /* CTAs per SM the backward is sized for (registers and shared memory) */
+#endif
+#if BWD_CTAS >= 3
+#define BWD_LIST_RECORDS 2560
+#else
 #define BWD_LIST_RECORDS 4096
+#endif
 #define BWD_MAXG 128
 
 struct BwdSmem {
     float4 rec[6][CHUNK];
     uint4 list[BWD_LIST_RECORDS];
-    float up[256][6];               // per pixel: dL/dcolor (3), dL/dnormal (3)
+    float4 up[2][256];              // per pixel: {dL/dcolor (3), dL/dnormal.x}, {dL/dnormal.yz, -, -}: two conflict-light LDS.128
     uint32_t id[CHUNK];
     int cnt[2][BWD_MAXG];
     int maxc;
@@ -354,9 +398,9 @@ __device__ __forceinline__ void bwd_phase_b(BwdSmem &sm, const int *cnt, int g0,
                 g[8] += dL_dz;
             }
             g[14] += G * dL_dalpha;
-            const float *up = sm.up[pix];
-            g[15] += w * up[0]; g[16] += w * up[1]; g[17] += w * up[2];
-            g[11] += w * up[3]; g[12] += w * up[4]; g[13] += w * up[5];
+            const float4 ua = sm.up[0][pix], ub = sm.up[1][pix];
+            g[15] += w * ua.x; g[16] += w * ua.y; g[17] += w * ua.z;
+            g[11] += w * ua.w; g[12] += w * ub.x; g[13] += w * ub.y;
         }
     }
     // all lanes of the warp take part in the shuffles; groups whose surfel recorded nothing carry zeros
@@ -369,7 +413,7 @@ __device__ __forceinline__ void bwd_phase_b(BwdSmem &sm, const int *cnt, int g0,
 
 // Two CTAs per SM (96 KB of shared memory, 128 registers).  Three per SM (2560-record lists, 80 registers) were
 // measured at 0.85 ms against 0.55 ms: the phase-A recurrences do not fit 80 registers (192 B of spills).
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(256, BWD_CTAS)
 render_bwd_kernel(RasterDims d, RasterWs ws, const float *__restrict__ bg,
                   const float *__restrict__ dL_dcolor, const float *__restrict__ dL_dallmap,
                   float *__restrict__ grad_acc)
@@ -412,16 +456,16 @@ render_bwd_kernel(RasterDims d, RasterWs ws, const float *__restrict__ bg,
         dn0 = ga[pix + 2 * HW]; dn1 = ga[pix + 3 * HW]; dn2 = ga[pix + 4 * HW];
         dL_dmedian = ga[pix + 5 * HW]; dL_dreg = ga[pix + 6 * HW];
     }
-    {
-        float *up = sm.up[pix_local];
-        up[0] = dpx0; up[1] = dpx1; up[2] = dpx2; up[3] = dn0; up[4] = dn1; up[5] = dn2;
-    }
+    sm.up[0][pix_local] = make_float4(dpx0, dpx1, dpx2, dn0);
+    sm.up[1][pix_local] = make_float4(dn1, dn2, 0.f, 0.f);
     const float final_D = inside ? fT[pix + HW] : 0.f, final_D2 = inside ? fT[pix + 2 * HW] : 0.f;
     const float final_A = 1 - T_final;
     const float bg_dot_dpixel = bg[0] * dpx0 + bg[1] * dpx1 + bg[2] * dpx2;
-    float ar0 = 0, ar1 = 0, ar2 = 0, lc0 = 0, lc1 = 0, lc2 = 0;
-    float last_alpha = 0, last_depth = 0, ln0 = 0, ln1 = 0, ln2 = 0;
-    float accum_depth_rec = 0, accum_alpha_rec = 0, an0 = 0, an1 = 0, an2 = 0, last_dL_dT = 0;
+    // Upstream keeps one suffix accumulator per output channel (colour 3, depth, alpha, normal 3), all with the same
+    // recurrence acc = last_alpha * last_value + (1 - last_alpha) * acc, and adds (value - acc) * dL/dchannel to
+    // dL/dalpha.  The sum over channels is linear, so ONE scalar recurrence on v = sum_ch value_ch * dL/dchannel does
+    // the same work (8 recurrences and ~20 registers less per pair).
+    float last_alpha = 0, v_last = 0, v_acc = 0, last_dL_dT = 0;
 
     // nothing behind the deepest contributor of the tile can receive gradient
     if (threadIdx.x == 0) sm.maxc = 0;
@@ -441,7 +485,7 @@ render_bwd_kernel(RasterDims d, RasterWs ws, const float *__restrict__ bg,
         const int lo = max(0, hi - CHUNK);
         const int cnt = hi - lo;
         // stage positions lo..hi-1; slot t holds position hi-1-t (back to front)
-        int big32 = 0, big64 = 0, big128 = 0;
+        int big0 = 0, big1 = 0, big2 = 0, big3 = 0;
         if ((int)threadIdx.x < cnt) {
             const uint32_t id = ws.ids[start + (hi - 1 - threadIdx.x)];
             sm.id[threadIdx.x] = id;
@@ -454,13 +498,16 @@ render_bwd_kernel(RasterDims d, RasterWs ws, const float *__restrict__ bg,
             const float y0 = fmaxf(q[4].z, (float)oy), y1 = fminf(q[4].w, (float)(oy + 15));
             const int wx = max(0, (int)floorf(x1) - (int)ceilf(x0) + 1), wy = max(0, (int)floorf(y1) - (int)ceilf(y0) + 1);
             const int area = wx * wy;
-            big32 = area > 32; big64 = area > 64; big128 = area > 128;
+            big0 = area > BWD_LIST_RECORDS / 128; big1 = area > BWD_LIST_RECORDS / 64;
+            big2 = area > BWD_LIST_RECORDS / 32; big3 = area > BWD_LIST_RECORDS / 16;
         }
-        const int any32 = __syncthreads_or(big32);
-        const int any64 = __syncthreads_or(big64);
-        const int any128 = __syncthreads_or(big128);
-        // list capacity per surfel = 4096 / G must cover the pixels of its cull box inside the tile
-        const int G = any128 ? 16 : (any64 ? 32 : (any32 ? 64 : 128));
+        const int any0 = __syncthreads_or(big0);
+        const int any1 = __syncthreads_or(big1);
+        const int any2 = __syncthreads_or(big2);
+        const int any3 = __syncthreads_or(big3);
+        // list capacity per surfel = BWD_LIST_RECORDS / G must cover the pixels of its cull box inside the tile
+        // (G = 8: capacity >= 256 = the whole tile)
+        const int G = any3 ? 8 : (any2 ? 16 : (any1 ? 32 : (any0 ? 64 : 128)));
         const int cap = BWD_LIST_RECORDS / G;
 
         for (int g0 = 0; g0 < cnt; g0 += G, parity ^= 1) {
@@ -500,30 +547,21 @@ render_bwd_kernel(RasterDims d, RasterWs ws, const float *__restrict__ bg,
                         const float inv1ma = fast_rcp(1.f - alpha);
                         T = T * inv1ma;
                         const float w = alpha * T;
-                        float dL_dalpha = 0.0f;
-                        ar0 = last_alpha * lc0 + (1.f - last_alpha) * ar0; lc0 = nr.w;
-                        ar1 = last_alpha * lc1 + (1.f - last_alpha) * ar1; lc1 = gb.x;
-                        ar2 = last_alpha * lc2 + (1.f - last_alpha) * ar2; lc2 = gb.y;
-                        dL_dalpha += (nr.w - ar0) * dpx0 + (gb.x - ar1) * dpx1 + (gb.y - ar2) * dpx2;
                         float dL_dz = 0.0f;
                         const float inv_cd = fast_rcp(c_d);
                         const float m_d = GA_M_C0 - GA_M_C1 * inv_cd;
                         const float dmd_dd = GA_M_C1 * inv_cd * inv_cd;
                         if (contributor == median_contributor - 1) dL_dz += dL_dmedian;
                         const float dL_dweight = (final_D2 + m_d * m_d * final_A - 2 * m_d * final_D) * dL_dreg;
-                        dL_dalpha += dL_dweight - last_dL_dT;
-                        last_dL_dT = dL_dweight * alpha + (1 - alpha) * last_dL_dT;
                         const float dL_dmd = 2.0f * (T * alpha) * (m_d * final_A - final_D) * dL_dreg;
                         dL_dz += dL_dmd * dmd_dd;
-                        accum_depth_rec = last_alpha * last_depth + (1.f - last_alpha) * accum_depth_rec;
-                        last_depth = c_d;
-                        dL_dalpha += (c_d - accum_depth_rec) * dL_ddepth;
-                        accum_alpha_rec = last_alpha + (1.f - last_alpha) * accum_alpha_rec;
-                        dL_dalpha += (1 - accum_alpha_rec) * dL_daccum;
-                        an0 = last_alpha * ln0 + (1.f - last_alpha) * an0; ln0 = nr.x;
-                        an1 = last_alpha * ln1 + (1.f - last_alpha) * an1; ln1 = nr.y;
-                        an2 = last_alpha * ln2 + (1.f - last_alpha) * an2; ln2 = nr.z;
-                        dL_dalpha += (nr.x - an0) * dn0 + (nr.y - an1) * dn1 + (nr.z - an2) * dn2;
+                        // v = (colour . dL/dcolour) + depth dL/ddepth + 1 dL/dalpha_acc + (normal . dL/dnormal)
+                        const float v = ((nr.w * dpx0 + gb.x * dpx1) + (gb.y * dpx2 + c_d * dL_ddepth)) +
+                                        ((nr.x * dn0 + nr.y * dn1) + (nr.z * dn2 + dL_daccum));
+                        v_acc = last_alpha * v_last + (1.f - last_alpha) * v_acc;
+                        v_last = v;
+                        float dL_dalpha = (v - v_acc) + (dL_dweight - last_dL_dT);
+                        last_dL_dT = dL_dweight * alpha + (1 - alpha) * last_dL_dT;
                         dL_dalpha *= T;
                         last_alpha = alpha;
                         dL_dalpha += (-T_final * inv1ma) * bg_dot_dpixel;
@@ -542,7 +580,7 @@ render_bwd_kernel(RasterDims d, RasterWs ws, const float *__restrict__ bg,
             if (G == 128) bwd_phase_b<2>(sm, cntp, g0, gcnt, cap, ox, oy, acc_base);
             else if (G == 64) bwd_phase_b<4>(sm, cntp, g0, gcnt, cap, ox, oy, acc_base);
             else if (G == 32) bwd_phase_b<8>(sm, cntp, g0, gcnt, cap, ox, oy, acc_base);
-            else bwd_phase_b<16>(sm, cntp, g0, gcnt, cap, ox, oy, acc_base);
+            else bwd_phase_b<16>(sm, cntp, g0, gcnt, cap, ox, oy, acc_base);     // G = 16, and G = 8 with half the threads idle
             __syncthreads();
         }
     }

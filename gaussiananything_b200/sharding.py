@@ -40,17 +40,27 @@ def group_pairs_by_sample(pairs):
 
 
 def render_sharded(renderer, local_surfels, cam_view, cam_view_proj, cam_pos, tanfov, group=None, **kw):
-    """local_surfels [1, P, 13] (this rank's decoded sample); cameras [S, V, ...] for ALL samples (replicated).
-    Returns {(b, v): dict of [C,H,W] tensors} for the pairs this rank owns."""
+    """local_surfels [S_local, P, 13] (this rank's decoded samples); cameras [S, V, ...] for ALL samples (replicated).
+    Returns {(b, v): dict of [C,H,W] tensors} for the pairs this rank owns.
+
+    The all-gather is the only collective; afterwards the rank's pairs are rendered with ONE batched rasteriser
+    call per distinct views-per-sample count (normally one call in total: samples that own the same number of
+    views form one [B', V'] batch of the kernels' (batch item, view) grid)."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     surfels = all_gather_surfels(local_surfels, group)            # [S, P, 13]
     S, V = cam_view.shape[:2]
+    by_sample = group_pairs_by_sample(shard_pairs(S, V, world, rank))
+    buckets = {}
+    for b, vs in by_sample.items():
+        buckets.setdefault(len(vs), []).append(b)
     result = {}
-    for b, vs in group_pairs_by_sample(shard_pairs(S, V, world, rank)).items():
-        idx = torch.tensor(vs, device=cam_view.device)
-        out = renderer.render(surfels[b:b + 1], cam_view[b:b + 1, idx], cam_view_proj[b:b + 1, idx],
-                              cam_pos[b:b + 1, idx], tanfov, **kw)
-        for j, v in enumerate(vs):
-            result[(b, v)] = {k: t[0, j] for k, t in out.items()}
+    for nv, samples in buckets.items():
+        bi = torch.tensor(samples, device=cam_view.device)
+        vi = torch.tensor([by_sample[b] for b in samples], device=cam_view.device)          # [B', nv]
+        rows = bi[:, None].expand(-1, nv)
+        out = renderer.render(surfels[bi], cam_view[rows, vi], cam_view_proj[rows, vi], cam_pos[rows, vi], tanfov, **kw)
+        for i, b in enumerate(samples):
+            for j, v in enumerate(by_sample[b]):
+                result[(b, v)] = {k: t[i, j] for k, t in out.items()}
     return result

@@ -36,15 +36,20 @@ def _worker(rank, world, port, q):
         allg = sharding.all_gather_surfels(local)
         ok = allg.shape == (world, 5, 13) and all(float(allg[r, 0, 1]) == r + 1 for r in range(world))
 
-        class FakeRenderer:            # records what the rank was asked to render
+        class FakeRenderer:            # records which (sample, camera) it was asked to pair
             def render(self, g, cv, cvp, cp, tanfov, **kw):
-                return {"image": g[:, :1, :1].expand(1, cv.shape[1], 1) + cv[:, :, 0, 0:1] * 0}
+                assert g.shape[0] == cv.shape[0]
+                return {"image": g[:, 0:1, 1:2] * 100.0 + cv[:, :, 0, 0:1]}               # [B', V', 1]
         S, V = world, 3
         cams = torch.zeros(S, V, 4, 4)
+        for b in range(S):
+            for v in range(V):
+                cams[b, v, 0, 0] = 10 * b + v
         res = sharding.render_sharded(FakeRenderer(), local, cams, cams, torch.zeros(S, V, 3), 0.36)
         mine = sharding.shard_pairs(S, V, world, rank)
         ok = ok and sorted(res.keys()) == sorted(mine)
-        ok = ok and all(float(res[(b, v)]["image"][0]) == 0.0 for (b, v) in mine)       # xyz column 0, row 0
+        # sample b came from rank b (marker b + 1) and was rendered with ITS camera (b, v)
+        ok = ok and all(float(res[(b, v)]["image"][0]) == (b + 1) * 100.0 + 10 * b + v for (b, v) in mine)
         q.put((rank, bool(ok)))
     finally:
         dist.destroy_process_group()
