@@ -416,6 +416,7 @@ def run_gpu(args):
         if world == 1 and not args.no_dit:
             try:
                 standin = run_gpu_standin(dev)
+                standin["speedup_raster_C2_vs_standin"] = value / standin["raster_C2"]["views_per_s"]
                 if isinstance(dit_leg, dict) and "ms_per_nfe" in dit_leg:
                     a = standin["dit_C3_B_N2048"]
                     best = min(v for k, v in a.items() if k.endswith("ms_per_nfe"))
@@ -741,11 +742,46 @@ def run_c5_leg(dev, world, rank, steps=20, cascade_samples=2, with_cascade=True)
     return out
 
 
+def run_raster_standin(dev, steps=20):
+    """The upstream rasteriser flow restated literally (baseline/raster_standin.cu): per-view launch sets with a
+    device->host read of num_rendered each, cub radix sort of the whole instance list, every pixel evaluates every
+    staged surfel, one atomicAdd per (pixel, surfel, gradient component).  Same C2 inputs as the headline."""
+    import torch
+    from baseline.raster_standin import StandinRasterizer
+    g, vs, ps = make_inputs(40)
+    r = StandinRasterizer(P_SURFELS, RES, RES, VIEWS, device=dev)
+    g13 = torch.tensor(g, device=dev)
+    vm, pm = torch.tensor(vs, device=dev), torch.tensor(ps, device=dev)
+    bg = torch.ones(3, device=dev)
+    torch.manual_seed(0)
+    dc, da = torch.randn(VIEWS, 3, RES, RES, device=dev), torch.randn(VIEWS, 7, RES, RES, device=dev)
+    flush = torch.empty(256 << 20, device=dev, dtype=torch.uint8)
+    for _ in range(3):
+        r.forward(g13, vm, pm, bg)
+        grad = r.backward(dc, da)
+    assert torch.isfinite(grad).all()
+    tot = 0.0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for _ in range(steps):
+        flush.zero_()
+        e0.record()
+        r.forward(g13, vm, pm, bg)
+        r.backward(dc, da)
+        e1.record()
+        e1.synchronize()
+        tot += e0.elapsed_time(e1)
+    ms = tot / steps
+    return {"what": "reference-algorithm GPU baseline: per-view launches + num_rendered read-back, global cub radix sort, "
+                    "dense per-tile evaluation, per-pair atomics (baseline/raster_standin.cu)",
+            "ms_per_step": ms, "views_per_s": VIEWS / (ms * 1e-3)}
+
+
 def run_gpu_standin(dev):
     """GPU comparison baselines on the same B200 (baseline/gpu_standin.py)."""
     from baseline import gpu_standin as gs
     out = {"what": "unfused PyTorch-CUDA restatement of the reference's DiT block stack: nn.Linear under bf16 autocast (cuBLAS) + "
                    "flash_attn_func + separate norm/modulate/GELU kernels, context K/V re-projected every block, 2B CFG forward"}
+    out["raster_C2"] = run_raster_standin(dev)
     out["dit_C3_B_N2048"] = gs.time_torch_dit(dev, 12, 768, 12, 2048, nfe=20)
     out["dit_deployed_L_N768"] = gs.time_torch_dit(dev, 24, 1024, 16, 768, nfe=20)
     return out

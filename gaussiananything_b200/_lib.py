@@ -17,7 +17,7 @@ _lib = None
 class GaRasterLayout(C.Structure):
     _fields_ = [(n, C.c_size_t) for n in (
         "total_bytes", "status", "rec", "depth", "rect", "tile_count", "tile_start",
-        "keys", "ids", "final_T", "n_contrib")]
+        "keys", "ids", "final_T", "n_contrib", "inst_off", "inst_cnt")]
 
 
 def lib():

@@ -13,14 +13,17 @@
 #include "raster_common.cuh"
 
 #define SCAN_THREADS 1024
+#define SORT_WARP_MAX 512          // tiles up to this many instances are sorted by a single warp in registers
 
 __global__ void __launch_bounds__(SCAN_THREADS)
 scan_tiles_kernel(RasterDims d, RasterWs ws)
 {
     __shared__ uint32_t s_warp[32];
     __shared__ uint32_t s_carry;
+    __shared__ int s_big;
     const int n = d.NV * d.T;
-    if (threadIdx.x == 0) s_carry = 0;
+    int big = 0;                                   // tiles of this thread that need the block-level sort
+    if (threadIdx.x == 0) { s_carry = 0; s_big = 0; }
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int base = 0; base < n; base += SCAN_THREADS) {
@@ -36,6 +39,7 @@ scan_tiles_kernel(RasterDims d, RasterWs ws)
             }
 #pragma unroll
             for (int q = 0; q < GA_TILE_REPLICAS; q++) v += rep[q];
+            big += v > SORT_WARP_MAX;
         }
         uint32_t x = v;
 #pragma unroll
@@ -73,11 +77,14 @@ scan_tiles_kernel(RasterDims d, RasterWs ws)
         if (threadIdx.x == SCAN_THREADS - 1) s_carry = excl + v;
         __syncthreads();
     }
+    if (big) atomicAdd(&s_big, big);
+    __syncthreads();
     if (threadIdx.x == 0) {
         const uint32_t total = s_carry;
         ws.tile_start[n] = total;
         ws.status[0] = (int32_t)total;
         ws.status[1] = ((int64_t)total > d.max_instances) ? 1 : 0;
+        ws.status[3] = s_big;                      // 0: sort_tiles_kernel has nothing to do and exits at once
     }
 }
 
@@ -136,7 +143,6 @@ __device__ __forceinline__ void block_bitonic_sort(unsigned long long *a, int n)
 }
 
 #define SORT_SMEM_KEYS 4096
-#define SORT_WARP_MAX 512          // tiles up to this many instances are sorted by a single warp in registers
 
 // Warp-level bitonic sort of up to 32*KPL keys held in registers, element i = r*32 + lane (striped, so global
 // loads/stores are coalesced): partner distances < 32 are shuffles, distances >= 32 stay inside the lane.
@@ -230,7 +236,7 @@ __global__ void __launch_bounds__(256)
 sort_tiles_kernel(RasterDims d, RasterWs ws)
 {
     __shared__ unsigned long long s_keys[SORT_SMEM_KEYS];
-    if (ws.status[1]) return;
+    if (ws.status[1] || ws.status[3] == 0) return;          // overflow, or no tile above the warp-sort limit
     const size_t tiles = (size_t)d.NV * d.T;
     for (size_t t = blockIdx.x; t < tiles; t += gridDim.x) {
         const uint32_t start = ws.tile_start[t], end = ws.tile_start[t + 1];

@@ -49,6 +49,17 @@ struct RasterWs {
     uint32_t *ids;
     float *final_T;
     int32_t *n_contrib;
+    uint32_t *inst_off;        // backward (split path): start of every instance's record slice
+    uint32_t *inst_cnt;        // ... and the number of records in it
+};
+
+// global-memory record lists of the split backward (carved from the backward scratch buffer)
+struct BwdLists {
+    uint32_t *tile_rec_start;  // [NV*T + 1] exclusive scan of the per-tile slice totals
+    int32_t *flag;             // [0] = 1: lists do not fit, fused kernel runs; [1] = records needed
+    uint4 *records;
+    uint32_t capacity;         // records the buffer holds
+    uint32_t *inst_off, *inst_cnt;
 };
 
 // kernel launchers (defined in the .cu files, called from raster_api.cu)
@@ -72,7 +83,7 @@ cudaError_t ga_launch_render_fwd(const RasterDims &d, const RasterWs &w, const f
                                  float *out_color, float *out_allmap, cudaStream_t s);
 cudaError_t ga_launch_render_bwd(const RasterDims &d, const RasterWs &w, const float *bg,
                                  const float *dL_dcolor, const float *dL_dallmap,
-                                 float *grad_acc, cudaStream_t s);
+                                 float *grad_acc, const BwdLists &lists, cudaStream_t s);
 cudaError_t ga_launch_preprocess_bwd(const RasterDims &d, const RasterWs &w, const float *gauss13,
                                      const float *viewmats, const float *projmats,
                                      const int32_t *radii, const float *grad_acc,

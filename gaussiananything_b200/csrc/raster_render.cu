@@ -18,7 +18,7 @@
 
 #define CHUNK 256
 #ifndef GA_FWD_GROUP_DEFAULT
-#define GA_FWD_GROUP_DEFAULT 32
+#define GA_FWD_GROUP_DEFAULT 8
 #endif
 
 // single-instruction approximations (MUFU.RCP / MUFU.EX2, <= 2 ulp): the IEEE division and the range-checked
@@ -84,9 +84,9 @@ __device__ __forceinline__ bool eval_pair(const float4 a, const float4 b, const 
 // (warp-uniform shared-memory reads).  With the C2 scene a surfel's cull box covers ~25 pixels, so only ~9 of the 32
 // lanes of a hit carry a contributing pixel.  GS = 16 splits the warp into two 4x4 blocks, GS = 8 into four 4x2
 // blocks; every group walks ITS OWN list of hits, so a round evaluates up to 32 / GS different surfels (2 or 4
-// distinct shared-memory addresses per load instead of one).  Measured on the C2 scene (tools/raster_rounds.py):
-// 33.9 rounds per warp and chunk with GS = 32, 24.6 with GS = 16, 20.1 with GS = 8 (13.5 with one list per lane, but
-// per-lane lists make every load a 32-address gather: 0.208 vs 0.199 ms in round 1).  Results do not depend on GS:
+// distinct shared-memory addresses per load instead of one).  C2 scene (tools/raster_rounds.py): 44 rounds per warp
+// and chunk with GS = 32, 32 with GS = 16, 26 with GS = 8 (17.5 with one list per lane, but per-lane lists make every
+// load a 32-address gather: 0.208 vs 0.199 ms in round 1).  Measured: 209 / 181 / 176 us per 6-view launch.  Results do not depend on GS:
 // the per-pixel sequence of contributing surfels is the same.
 template <int GS>
 __global__ void __launch_bounds__(256, 4)
@@ -271,6 +271,12 @@ cudaError_t ga_launch_render_fwd(const RasterDims &d, const RasterWs &w, const f
 #define BWD_LIST_RECORDS 4096
 #endif
 #define BWD_MAXG 128
+#ifndef BWD_A_CTAS
+#define BWD_A_CTAS 3                /* resident CTAs per SM kernel A is compiled for */
+#endif
+#ifndef BWD_B_TPI
+#define BWD_B_TPI 4                 /* lanes per instance in kernel B */
+#endif
 
 struct BwdSmem {
     float4 rec[6][CHUNK];
@@ -416,11 +422,12 @@ __device__ __forceinline__ void bwd_phase_b(BwdSmem &sm, const int *cnt, int g0,
 __global__ void __launch_bounds__(256, BWD_CTAS)
 render_bwd_kernel(RasterDims d, RasterWs ws, const float *__restrict__ bg,
                   const float *__restrict__ dL_dcolor, const float *__restrict__ dL_dallmap,
-                  float *__restrict__ grad_acc)
+                  float *__restrict__ grad_acc, const int32_t *__restrict__ split_flag)
 {
     extern __shared__ __align__(16) uint8_t bwd_smem_raw[];
     BwdSmem &sm = *reinterpret_cast<BwdSmem *>(bwd_smem_raw);
     if (ws.status[1]) return;
+    if (split_flag && split_flag[0] == 0) return;      // the split kernels (below) did the work
     const int view = blockIdx.z;
     const int tile = blockIdx.y * d.gx + blockIdx.x;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -513,7 +520,9 @@ render_bwd_kernel(RasterDims d, RasterWs ws, const float *__restrict__ bg,
         for (int g0 = 0; g0 < cnt; g0 += G, parity ^= 1) {
             const int gcnt = min(G, cnt - g0);
             int *cntp = sm.cnt[parity];
-            // ---------------- phase A: sub-blocks of 32 surfels, no block barrier in between
+            // ---------------- phase A: sub-blocks of 32 surfels, no block barrier in between.  (Walking one per-lane
+            // list over the whole group of 128 instead needs 22 % fewer rounds, tools/raster_rounds.py, but was measured
+            // slower: 573 vs 537 us -- the list bookkeeping costs more than the rounds it saves.)
             for (int sb = 0; sb < gcnt; sb += 32) {
                 const int base = g0 + sb;
                 bool hit = false;
@@ -586,9 +595,354 @@ render_bwd_kernel(RasterDims d, RasterWs ws, const float *__restrict__ bg,
     }
 }
 
+// ---------------------------------------------------------------------------
+// K4 split variant (default): the two phases as two kernels, with the per-(tile, surfel) record lists in GLOBAL
+// memory (the fused kernel above remains the fallback when the list budget does not cover the scene).
+//
+// Why: in the fused kernel the lists live in 64 KB of shared memory and both phases share one register budget
+// (125 registers, 2 CTAs = 16 warps per SM); its top stall reason is the block barrier between the phases
+// (profiles/r02_raster.md: barrier 2.1, wait 1.7 warps per issue at 47 % issue utilisation).  HBM, on the other
+// hand, is idle (5 % DRAM utilisation).  So:
+//   kernel A (pixel-parallel, back to front)  = phase A; records go to the instance's slice of a global buffer.
+//     The slice length is the instance's cull-box area inside the tile -- exact, so there is no capacity rule, no
+//     group size G, no phase-B barrier: three block barriers per chunk of 256 surfels instead of seven.
+//   kernel B (instance-parallel)              = phase B; TPI lanes walk an instance's records (contiguous 16-byte
+//     entries), re-derive the geometry with the same eval_pair() (same bits), reduce-scatter, global atomics.
+// Slices are laid out tile by tile: a warp-per-tile pre-pass sums the clipped cull-box areas, one block scans the
+// tile totals.  If the total exceeds the buffer, a device flag routes the launch to the fused kernel instead (no
+// host synchronisation either way).  Extra traffic: 16 B written + read per record, ~2 x 26 M records on C2.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ int clipped_box_area(const float4 bb, int ox, int oy)
+{
+    const float x0 = fmaxf(bb.x, (float)ox), x1 = fminf(bb.y, (float)(ox + 15));
+    const float y0 = fmaxf(bb.z, (float)oy), y1 = fminf(bb.w, (float)(oy + 15));
+    const int wx = max(0, (int)floorf(x1) - (int)ceilf(x0) + 1), wy = max(0, (int)floorf(y1) - (int)ceilf(y0) + 1);
+    return wx * wy;
+}
+
+// one warp per tile: sum of the clipped cull-box areas of the tile's instances
+__global__ void __launch_bounds__(256)
+bwd_tile_area_kernel(RasterDims d, RasterWs ws, BwdLists L)
+{
+    if (ws.status[1]) return;
+    const size_t t = (size_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (t >= (size_t)d.NV * d.T) return;
+    const int lane = threadIdx.x & 31;
+    const int view = (int)(t / d.T), tile = (int)(t % d.T);
+    const int ox = (tile % d.gx) * GA_BLOCK_X, oy = (tile / d.gx) * GA_BLOCK_Y;
+    const uint32_t start = ws.tile_start[t], end = ws.tile_start[t + 1];
+    const float *rec_base = ws.rec + (size_t)view * d.P * GA_REC_F;
+    uint32_t sum = 0;
+    for (uint32_t i = start + lane; i < end; i += 32) {
+        const float4 bb = __ldg(reinterpret_cast<const float4 *>(rec_base + (size_t)ws.ids[i] * GA_REC_F) + 4);
+        sum += (uint32_t)clipped_box_area(bb, ox, oy);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if (lane == 0) L.tile_rec_start[t] = sum;
+}
+
+// exclusive scan of the tile totals (one block); sets the fallback flag when the buffer is too small
+__global__ void __launch_bounds__(1024)
+bwd_scan_area_kernel(RasterDims d, RasterWs ws, BwdLists L)
+{
+    __shared__ uint32_t s_warp[32];
+    __shared__ uint32_t s_carry;
+    if (ws.status[1]) return;
+    const int n = d.NV * d.T;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int base = 0; base < n; base += 1024) {
+        const int i = base + threadIdx.x;
+        const uint32_t v = i < n ? L.tile_rec_start[i] : 0u;
+        uint32_t x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o) x += y;
+        }
+        if (lane == 31) s_warp[warp] = x;
+        __syncthreads();
+        if (warp == 0) {
+            const uint32_t wv = s_warp[lane];
+            uint32_t wx = wv;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xffffffffu, wx, o);
+                if (lane >= o) wx += y;
+            }
+            s_warp[lane] = wx - wv;
+        }
+        __syncthreads();
+        const uint32_t excl = s_carry + s_warp[warp] + x - v;
+        if (i < n) L.tile_rec_start[i] = excl;
+        __syncthreads();
+        if (threadIdx.x == 1023) s_carry = excl + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        L.tile_rec_start[n] = s_carry;
+        L.flag[0] = (s_carry > L.capacity) ? 1 : 0;       // 1: lists do not fit -> the fused kernel runs instead
+        L.flag[1] = (int32_t)s_carry;
+    }
+}
+
+struct BwdASmem {
+    float4 rec[6][CHUNK];
+    uint32_t off[CHUNK];            // start of the instance's slice, relative to the tile's base
+    int cnt[CHUNK];
+    uint32_t wsum[8];
+    int maxc;
+};
+
+__global__ void __launch_bounds__(256, BWD_A_CTAS)
+render_bwd_a_kernel(RasterDims d, RasterWs ws, BwdLists L, const float *__restrict__ bg,
+                    const float *__restrict__ dL_dcolor, const float *__restrict__ dL_dallmap)
+{
+    __shared__ BwdASmem sm;
+    if (ws.status[1] || L.flag[0]) return;
+    const int view = blockIdx.z;
+    const int tile = blockIdx.y * d.gx + blockIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ox = blockIdx.x * GA_BLOCK_X, oy = blockIdx.y * GA_BLOCK_Y;
+    const int lx0 = (warp & 1) * 8, ly0 = (warp >> 1) * 4;
+    const int lxi = lx0 + (lane & 7), lyi = ly0 + (lane >> 3);
+    const int pxi = ox + lxi, pyi = oy + lyi;
+    const int pix_local = lyi * 16 + lxi;
+    const bool inside = pxi < d.W && pyi < d.H;
+    const float pfx = (float)pxi, pfy = (float)pyi;
+    const float bx_lo = (float)(ox + lx0), bx_hi = (float)(ox + lx0 + 7);
+    const float by_lo = (float)(oy + ly0), by_hi = (float)(oy + ly0 + 3);
+
+    const size_t gt = (size_t)view * d.T + tile;
+    const uint32_t start = ws.tile_start[gt];
+    const uint32_t tile_base = L.tile_rec_start[gt];
+    const size_t HW = (size_t)d.H * d.W;
+    const size_t pix = inside ? (size_t)pyi * d.W + pxi : 0;
+    const float *fT = ws.final_T + (size_t)view * 3 * HW;
+    const int32_t *nc = ws.n_contrib + (size_t)view * 2 * HW;
+    const float *rec_base = ws.rec + (size_t)view * d.P * GA_REC_F;
+
+    const float T_final = inside ? fT[pix] : 0.f;
+    float T = T_final;
+    const int last_contributor = inside ? nc[pix] : 0;
+    const int median_contributor = inside ? nc[pix + HW] : 0;
+    float dpx0 = 0, dpx1 = 0, dpx2 = 0, dL_ddepth = 0, dL_daccum = 0, dL_dreg = 0;
+    float dn0 = 0, dn1 = 0, dn2 = 0, dL_dmedian = 0;
+    if (inside) {
+        const float *gc = dL_dcolor + (size_t)view * 3 * HW;
+        const float *ga = dL_dallmap + (size_t)view * 7 * HW;
+        dpx0 = gc[pix]; dpx1 = gc[pix + HW]; dpx2 = gc[pix + 2 * HW];
+        dL_ddepth = ga[pix]; dL_daccum = ga[pix + HW];
+        dn0 = ga[pix + 2 * HW]; dn1 = ga[pix + 3 * HW]; dn2 = ga[pix + 4 * HW];
+        dL_dmedian = ga[pix + 5 * HW]; dL_dreg = ga[pix + 6 * HW];
+    }
+    const float final_D = inside ? fT[pix + HW] : 0.f, final_D2 = inside ? fT[pix + 2 * HW] : 0.f;
+    const float final_A = 1 - T_final;
+    const float bg_dot_dpixel = bg[0] * dpx0 + bg[1] * dpx1 + bg[2] * dpx2;
+    float last_alpha = 0, v_last = 0, v_acc = 0, last_dL_dT = 0;        // one scalar suffix recurrence (see the fused kernel)
+
+    if (threadIdx.x == 0) sm.maxc = 0;
+    __syncthreads();
+    {
+        int m = last_contributor;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+        if (lane == 0) atomicMax(&sm.maxc, m);
+    }
+    __syncthreads();
+    const int total = sm.maxc;          // list positions [0,total) matter; the rest keep inst_cnt == 0 (memset)
+    uint32_t run = 0;                   // records handed out to the chunks staged so far
+
+    for (int hi = total; hi > 0; hi -= CHUNK) {
+        const int lo = max(0, hi - CHUNK);
+        const int cnt = hi - lo;
+        // stage positions lo..hi-1; slot t holds position hi-1-t (back to front); slice length = clipped box area
+        uint32_t area = 0;
+        if ((int)threadIdx.x < cnt) {
+            const uint32_t id = ws.ids[start + (hi - 1 - threadIdx.x)];
+            const float4 *src = reinterpret_cast<const float4 *>(rec_base + (size_t)id * GA_REC_F);
+            float4 q[6];
+#pragma unroll
+            for (int k = 0; k < 6; k++) { q[k] = __ldg(src + k); sm.rec[k][threadIdx.x] = q[k]; }
+            area = (uint32_t)clipped_box_area(q[4], ox, oy);
+        }
+        uint32_t x = area;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o) x += y;
+        }
+        if (lane == 31) sm.wsum[warp] = x;
+        __syncthreads();
+        uint32_t wbase = 0, chunk_total = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) { const uint32_t wv = sm.wsum[k]; if (k < warp) wbase += wv; chunk_total += wv; }
+        const uint32_t my_off = run + wbase + x - area;
+        sm.off[threadIdx.x] = my_off;
+        sm.cnt[threadIdx.x] = 0;
+        if ((int)threadIdx.x < cnt) L.inst_off[start + (hi - 1 - threadIdx.x)] = tile_base + my_off;
+        __syncthreads();
+
+        for (int sb = 0; sb < cnt; sb += 32) {
+            bool hit = false;
+            if (sb + lane < cnt) {
+                const float4 bb = sm.rec[4][sb + lane];
+                hit = !(bb.y < bx_lo || bb.x > bx_hi || bb.w < by_lo || bb.z > by_hi);
+            }
+            unsigned mask = __ballot_sync(0xffffffffu, hit);
+            unsigned mine = 0;
+            while (mask) {
+                const int b = __ffs(mask) - 1;
+                mask &= mask - 1;
+                const float4 bb = sm.rec[4][sb + b];
+                if (pfx >= bb.x && pfx <= bb.y && pfy >= bb.z && pfy <= bb.w && (hi - 1 - (sb + b)) < last_contributor)
+                    mine |= 1u << b;
+            }
+            if (!inside) mine = 0;
+            while (__any_sync(0xffffffffu, mine != 0)) {
+                const bool active = mine != 0;
+                const int bsel = active ? __ffs(mine) - 1 : 0;
+                mine &= mine - 1;
+                const int jj = sb + bsel;
+                const int contributor = hi - 1 - jj;       // 0-based list position
+                const float4 a = sm.rec[0][jj], b = sm.rec[1][jj], c = sm.rec[2][jj];
+                PixelGeom pg;
+                float k0, k1, k2, l0, l1, l2;
+                const bool ok = active && eval_pair(a, b, c, pfx, pfy, pg, k0, k1, k2, l0, l1, l2);
+                if (ok) {
+                    const float4 nr = sm.rec[3][jj], gb = sm.rec[5][jj];
+                    const float alpha = pg.alpha, c_d = pg.depth;
+                    const float inv1ma = fast_rcp(1.f - alpha);
+                    T = T * inv1ma;
+                    const float w = alpha * T;
+                    float dL_dz = 0.0f;
+                    const float inv_cd = fast_rcp(c_d);
+                    const float m_d = GA_M_C0 - GA_M_C1 * inv_cd;
+                    const float dmd_dd = GA_M_C1 * inv_cd * inv_cd;
+                    if (contributor == median_contributor - 1) dL_dz += dL_dmedian;
+                    const float dL_dweight = (final_D2 + m_d * m_d * final_A - 2 * m_d * final_D) * dL_dreg;
+                    const float dL_dmd = 2.0f * (T * alpha) * (m_d * final_A - final_D) * dL_dreg;
+                    dL_dz += dL_dmd * dmd_dd;
+                    const float v = ((nr.w * dpx0 + gb.x * dpx1) + (gb.y * dpx2 + c_d * dL_ddepth)) +
+                                    ((nr.x * dn0 + nr.y * dn1) + (nr.z * dn2 + dL_daccum));
+                    v_acc = last_alpha * v_last + (1.f - last_alpha) * v_acc;
+                    v_last = v;
+                    float dL_dalpha = (v - v_acc) + (dL_dweight - last_dL_dT);
+                    last_dL_dT = dL_dweight * alpha + (1 - alpha) * last_dL_dT;
+                    dL_dalpha *= T;
+                    last_alpha = alpha;
+                    dL_dalpha += (-T_final * inv1ma) * bg_dot_dpixel;
+                    dL_dz += w * dL_ddepth;
+                    const int slot = atomicAdd(&sm.cnt[jj], 1);          // < the instance's clipped box area by construction
+                    L.records[(size_t)tile_base + sm.off[jj] + (uint32_t)slot] =
+                        make_uint4((uint32_t)pix_local, __float_as_uint(dL_dalpha), __float_as_uint(dL_dz), __float_as_uint(w));
+                }
+            }
+        }
+        __syncthreads();
+        if ((int)threadIdx.x < cnt) L.inst_cnt[start + (hi - 1 - threadIdx.x)] = (uint32_t)sm.cnt[threadIdx.x];
+        run += chunk_total;
+        // sm.rec / off / cnt are rewritten by the next chunk's staging only after every thread passed the barrier above
+        // and read its own cnt entry -- the staging below writes rec first, and off/cnt after its own barrier
+    }
+}
+
+template <int TPI>
+__global__ void __launch_bounds__(256)
+render_bwd_b_kernel(RasterDims d, RasterWs ws, BwdLists L, const float *__restrict__ dL_dcolor,
+                    const float *__restrict__ dL_dallmap, float *__restrict__ grad_acc)
+{
+    __shared__ float4 s_up[2][256];
+    if (ws.status[1] || L.flag[0]) return;
+    const int view = blockIdx.z;
+    const int tile = blockIdx.y * d.gx + blockIdx.x;
+    const int ox = blockIdx.x * GA_BLOCK_X, oy = blockIdx.y * GA_BLOCK_Y;
+    const size_t gt = (size_t)view * d.T + tile;
+    const uint32_t start = ws.tile_start[gt], end = ws.tile_start[gt + 1];
+    const int total = (int)(end - start);
+    if (total == 0) return;
+    {
+        const int lxi = threadIdx.x & 15, lyi = threadIdx.x >> 4;
+        const int pxi = ox + lxi, pyi = oy + lyi;
+        float4 ua = make_float4(0.f, 0.f, 0.f, 0.f), ub = ua;
+        if (pxi < d.W && pyi < d.H) {
+            const size_t HW = (size_t)d.H * d.W, pix = (size_t)pyi * d.W + pxi;
+            const float *gc = dL_dcolor + (size_t)view * 3 * HW;
+            const float *ga = dL_dallmap + (size_t)view * 7 * HW;
+            ua = make_float4(gc[pix], gc[pix + HW], gc[pix + 2 * HW], ga[pix + 2 * HW]);
+            ub = make_float4(ga[pix + 3 * HW], ga[pix + 4 * HW], 0.f, 0.f);
+        }
+        s_up[0][threadIdx.x] = ua;              // index = ly * 16 + lx = the records' pixel field
+        s_up[1][threadIdx.x] = ub;
+    }
+    __syncthreads();
+    const float *rec_base = ws.rec + (size_t)view * d.P * GA_REC_F;
+    float *acc_base = grad_acc + (size_t)view * d.P * GA_GRAD_F;
+    const int lane = threadIdx.x & 31;
+    const int sub = threadIdx.x % TPI;
+    constexpr int IPB = 256 / TPI;              // instances per pass
+    for (int base = 0; base < total; base += IPB) {
+        const int inst = base + threadIdx.x / TPI;
+        const bool valid = inst < total;
+        const int n = valid ? (int)L.inst_cnt[start + inst] : 0;
+        float g[GA_GRAD_F];
+#pragma unroll
+        for (int f = 0; f < GA_GRAD_F; f++) g[f] = 0.f;
+        uint32_t id = 0;
+        if (n > 0) {
+            id = ws.ids[start + inst];
+            const float4 *src = reinterpret_cast<const float4 *>(rec_base + (size_t)id * GA_REC_F);
+            const float4 a = __ldg(src), b = __ldg(src + 1), c = __ldg(src + 2);
+            const float opa = c.w;
+            const uint4 *lst = L.records + L.inst_off[start + inst];
+            for (int r = sub; r < n; r += TPI) {
+                const uint4 rc = lst[r];
+                const int pix = (int)rc.x;
+                const float dL_dalpha = __uint_as_float(rc.y), dL_dz = __uint_as_float(rc.z), w = __uint_as_float(rc.w);
+                const float pfx = (float)(ox + (pix & 15)), pfy = (float)(oy + (pix >> 4));
+                PixelGeom pg;
+                float k0, k1, k2, l0, l1, l2;
+                eval_pair(a, b, c, pfx, pfy, pg, k0, k1, k2, l0, l1, l2);      // same code path as kernel A: same bits
+                const float G = pg.G;
+                const float dL_dG = opa * dL_dalpha;                           // 0.99 clamp passed through (upstream)
+                if (pg.use3d) {
+                    const float dL_ds0 = dL_dG * -G * pg.s0 + dL_dz * b.z;
+                    const float dL_ds1 = dL_dG * -G * pg.s1 + dL_dz * b.w;
+                    const float ip = fast_rcp(pg.p2);
+                    const float q0 = dL_ds0 * ip, q1 = dL_ds1 * ip;
+                    const float q2 = -(q0 * pg.s0 + q1 * pg.s1);
+                    const float dk0 = l1 * q2 - l2 * q1, dk1 = l2 * q0 - l0 * q2, dk2 = l0 * q1 - l1 * q0;
+                    const float dl0 = q1 * k2 - q2 * k1, dl1 = q2 * k0 - q0 * k2, dl2 = q0 * k1 - q1 * k0;
+                    g[0] -= dk0; g[1] -= dk1; g[2] -= dk2;
+                    g[3] -= dl0; g[4] -= dl1; g[5] -= dl2;
+                    g[6] += pfx * dk0 + pfy * dl0 + dL_dz * pg.s0;
+                    g[7] += pfx * dk1 + pfy * dl1 + dL_dz * pg.s1;
+                    g[8] += pfx * dk2 + pfy * dl2 + dL_dz;
+                } else {
+                    g[9] += dL_dG * (-G * GA_FILTER_INV_SQUARE * pg.dx);
+                    g[10] += dL_dG * (-G * GA_FILTER_INV_SQUARE * pg.dy);
+                    g[8] += dL_dz;
+                }
+                g[14] += G * dL_dalpha;
+                const float4 ua = s_up[0][pix], ub = s_up[1][pix];
+                g[15] += w * ua.x; g[16] += w * ua.y; g[17] += w * ua.z;
+                g[11] += w * ua.w; g[12] += w * ub.x; g[13] += w * ub.y;
+            }
+        }
+        if (__any_sync(0xffffffffu, n > 0)) {
+            float *dst = acc_base + (size_t)id * GA_GRAD_F;          // lanes without records carry zeros (id 0, adds skipped)
+            reduce_scatter18<TPI>(g, lane, dst);
+        }
+    }
+}
+
+static int g_bwd_split = -1;
+
 cudaError_t ga_launch_render_bwd(const RasterDims &d, const RasterWs &w, const float *bg,
                                  const float *dL_dcolor, const float *dL_dallmap,
-                                 float *grad_acc, cudaStream_t s)
+                                 float *grad_acc, const BwdLists &lists, cudaStream_t s)
 {
     static GaPerDevice attr_set;
     if (ga_first_use_on_device(attr_set)) {
@@ -596,7 +950,21 @@ cudaError_t ga_launch_render_bwd(const RasterDims &d, const RasterWs &w, const f
                                              (int)sizeof(BwdSmem));
         if (e != cudaSuccess) return e;
     }
+    if (g_bwd_split < 0) {
+        const char *e = getenv("GA_B200_BWD_SPLIT");        // 0: always the fused kernel (A/B comparisons)
+        g_bwd_split = (e && e[0] == '0') ? 0 : 1;
+    }
     dim3 grid(d.gx, d.gy, d.NV);
-    render_bwd_kernel<<<grid, 256, sizeof(BwdSmem), s>>>(d, w, bg, dL_dcolor, dL_dallmap, grad_acc);
+    const bool split = g_bwd_split && lists.records && lists.capacity > 0;
+    if (split) {
+        const int tiles = d.NV * d.T;
+        bwd_tile_area_kernel<<<(tiles + 7) / 8, 256, 0, s>>>(d, w, lists);
+        bwd_scan_area_kernel<<<1, 1024, 0, s>>>(d, w, lists);
+        render_bwd_a_kernel<<<grid, 256, 0, s>>>(d, w, lists, bg, dL_dcolor, dL_dallmap);
+        render_bwd_b_kernel<BWD_B_TPI><<<grid, 256, 0, s>>>(d, w, lists, dL_dcolor, dL_dallmap, grad_acc);
+    }
+    // fused kernel: the whole job when the split path is off, a no-op (flag == 0) or the fallback (flag == 1) otherwise
+    render_bwd_kernel<<<grid, 256, sizeof(BwdSmem), s>>>(d, w, bg, dL_dcolor, dL_dallmap, grad_acc,
+                                                         split ? lists.flag : nullptr);
     return cudaGetLastError();
 }

@@ -260,3 +260,96 @@ def decode_flops(D=768, depth=12, N=None):
     blk = lambda Ls: 2 * Ls * D * (3 * D + D + 8 * D) + 4 * Ls * Ls * D
     d1 = depth // 6 if depth == 12 else 2
     return (depth * (blk(N) + 2 * N * D * 6 * D) + N * d1 * blk(9) + N * 8 * blk(5) + N * 32 * blk(4))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Drop-in for the reference's auto-encoder wrapper on the decode / render behaviours
+# ---------------------------------------------------------------------------------------------------------------
+class SurfelAE:
+    """Mirror of `nsr.script_util.AE.forward` (/root/reference/nsr/script_util.py:300-367) for the behaviours the
+    sampling pipeline uses after the DiT (/root/reference/nsr/lsgm/flow_matching_trainer.py:1399-1424,1545-1567):
+
+      rec_model(latent={'latent_normalized': [B,N,Cz], 'query_pcd_xyz': [B,N,3]}, behaviour='decode_gs_after_vae_no_render')
+      rec_model(img=None, c=c, latent=ret, behaviour='triplane_dec', bg_color=..., render_all_scale=True)
+      rec_model(latent=..., c=c, behaviour='decode_after_vae')
+
+    `triplane_decode` (/root/reference/vit/vit_triplane.py:1550-1591) renders every level of detail of the cascade --
+    gaussians_base 128^2, gaussians_upsampled 256^2, _2 384^2, _3 512^2 -- for all B x V cameras.  The reference
+    issues 4 x B x V sequential launch sets from Python; here every level is ONE batched launch set and the four
+    levels run on four CUDA streams, so the small levels (768 / 6 144 / 24 576 surfels: latency bound) overlap with
+    the 73 728-surfel one.  The encoder behaviours ('enc', 'enc_dec', ...) are out of scope and raise."""
+
+    OUTPUT_SIZE = {"gaussians_base": 128, "gaussians_upsampled": 256, "gaussians_upsampled_2": 384,
+                   "gaussians_upsampled_3": 512}
+
+    def __init__(self, decoder, renderer=None, img_size=None, rand_base_render=True, rendering_kwargs=None):
+        from .gs_surfel import GaussianRenderer2DGS
+        self.decoder = decoder
+        self.img_size = img_size
+        self.output_size = dict(self.OUTPUT_SIZE)
+        self.rand_base_render = rand_base_render
+        self.rendering_kwargs = rendering_kwargs or {}
+        self.gs = renderer if renderer is not None else GaussianRenderer2DGS(512, 3, self.rendering_kwargs)
+        self._streams = None
+
+    # ---- reference method names
+    def decode_after_vae_no_render(self, ret_dict, img_size=None):
+        lat = ret_dict["latent_normalized"] if isinstance(ret_dict, dict) else ret_dict
+        out = dict(ret_dict) if isinstance(ret_dict, dict) else {}
+        out.update(self.decoder.decode(lat, ret_dict["query_pcd_xyz"]))
+        return out
+
+    def decode_after_vae_no_render_gs(self, ret_dict, img_size=None):
+        return self.decode_after_vae_no_render(ret_dict, img_size)          # decode() already applies forward_gaussians
+
+    def decode_after_vae(self, ret_dict, c, img_size=None, return_raw_only=False):
+        return self.triplane_decode(self.decode_after_vae_no_render(ret_dict, img_size), c)
+
+    def triplane_decode(self, ret_after_gaussian_forward, c, bg_color=None, render_all_scale=False, **kwargs):
+        import random
+        keys = list(self.output_size.keys())
+        if self.rand_base_render and not render_all_scale:
+            keys = [random.choice(keys[:-1])] + [keys[-1]]
+        dev = ret_after_gaussian_forward[keys[-1]].device
+        main = torch.cuda.current_stream(dev)
+        if self._streams is None or self._streams[0].device != dev:
+            self._streams = [torch.cuda.Stream(dev) for _ in range(len(self.output_size))]
+        tanfov = c["tanfov"]
+        tanfov = float(tanfov) if not isinstance(tanfov, float) else tanfov
+        fork = torch.cuda.Event()
+        fork.record(main)
+        results = {}
+        # largest level first: it is the long pole, the small ones fill in beside it
+        for i, key in enumerate(sorted(keys, key=lambda k: -self.output_size[k])):
+            s = self._streams[i]
+            s.wait_event(fork)
+            with torch.cuda.stream(s):
+                r = self.gs.render(ret_after_gaussian_forward[key], c["cam_view"], c["cam_view_proj"], c["cam_pos"],
+                                   tanfov=tanfov, bg_color=bg_color, output_size=self.output_size[key])
+                r["image_raw"] = r["image"] * 2 - 1                      # [0,1] -> [-1,1] (vit_triplane.py:1570-1573)
+                r["image_depth"] = r["depth"]
+                r["image_mask"] = r["alpha"]
+                for t in r.values():
+                    t.record_stream(main)
+            results[key] = r
+        for s in self._streams:
+            main.wait_stream(s)
+        return {k: results[k] for k in keys}                              # the reference's key order
+
+    def forward(self, img=None, c=None, latent=None, behaviour="enc_dec", coordinates=None, directions=None,
+                return_raw_only=False, *args, **kwargs):
+        if behaviour == "decode_gs_after_vae_no_render":
+            return self.decode_after_vae_no_render_gs(latent, self.img_size)
+        if behaviour == "decode_after_vae_no_render":
+            return self.decode_after_vae_no_render(latent, self.img_size)
+        if behaviour == "decode_after_vae":
+            return self.decode_after_vae(latent, c, self.img_size)
+        if behaviour == "triplane_dec":
+            assert latent is not None
+            return self.triplane_decode(latent, c, **kwargs)
+        if behaviour == "get_rendering_kwargs":
+            return self.rendering_kwargs
+        raise NotImplementedError("gaussiananything_b200.SurfelAE: behaviour %r is outside the decode / render path "
+                                  "(encoder and training behaviours are not rebuilt: SURVEY.md section 8)" % (behaviour,))
+
+    __call__ = forward

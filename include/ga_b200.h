@@ -48,6 +48,8 @@ typedef struct GaRasterLayout {
     size_t ids;         /* uint32[max_instances]  sorted surfel index per instance */
     size_t final_T;     /* float[NV][3][H*W]  T, M1, M2 */
     size_t n_contrib;   /* int32[NV][2][H*W]  last contributor, median contributor */
+    size_t inst_off;    /* uint32[max_instances]  backward: start of the instance's record slice */
+    size_t inst_cnt;    /* uint32[max_instances]  backward: records in it */
 } GaRasterLayout;
 
 /* Fills *layout for NV = batch*views images of H x W, P surfels per batch item
@@ -123,7 +125,16 @@ int ga_render_post_backward(const float *color, const float *allmap, const float
 int ga_raster_set_variant(int radius_formula, int quat_norm_grad);
 int ga_raster_get_variant(int *radius_formula, int *quat_norm_grad);
 
-/* Bytes of scratch the backward needs (gradient accumulators). */
+/*
+ * Scheduling knob of the forward composite (results do not depend on it): lanes per group that walks its own list of
+ * hits inside a warp's 8x4 pixel block -- 32 (one surfel per warp round), 16 or 8 (default; env GA_B200_FWD_GROUP).
+ * Returns -1 for any other value.
+ */
+int ga_raster_set_tuning(int fwd_group);
+
+/* Bytes of scratch the backward wants: gradient accumulators [NV*P][18] (mandatory) + the global record lists of
+ * the split backward (64 records of 16 bytes per (surfel, view)).  A smaller buffer that still holds the
+ * accumulators is accepted: the backward then runs its fused shared-memory kernel. */
 size_t ga_raster_backward_scratch_bytes(int batch, int P, int views);
 
 /*

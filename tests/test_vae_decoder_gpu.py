@@ -80,3 +80,42 @@ def test_surfel_decoder_deployed_size_properties():
     assert torch.equal(out2["gaussians_upsampled_3"], s)
     out3 = dec.decode(lat.flip(0).contiguous(), xyz.flip(0).contiguous())
     assert rel(out3["gaussians_upsampled_3"].flip(0), s) < 1e-5
+
+
+
+def test_surfel_ae_dropin_behaviours_and_multi_lod_render():
+    """SurfelAE mirrors nsr.script_util.AE.forward on the decode / render behaviours; triplane_decode renders the
+    four levels of detail (one batched launch set each, on four streams) == rendering each level on its own."""
+    from gaussiananything_b200.gs_surfel import GaussianRenderer2DGS
+    from gaussiananything_b200.vae_decoder import SurfelAE, SurfelDecoder, random_state_dict
+    from tests.helpers import cameras
+    dev = torch.device("cuda:0")
+    D, depth = 128, 2
+    dec = SurfelDecoder(random_state_dict(D, depth, 10, seed=3), D // 64, depth, device=dev)
+    ae = SurfelAE(dec)
+    torch.manual_seed(0)
+    B, V = 2, 3
+    lat = {"latent_normalized": torch.randn(B, D, 10, device=dev), "query_pcd_xyz": (torch.rand(B, D, 3, device=dev) - 0.5) * 0.6}
+    ret = ae(latent=lat, behaviour="decode_gs_after_vae_no_render")
+    for k, f in (("gaussians_base", 1), ("gaussians_upsampled", 8), ("gaussians_upsampled_2", 32), ("gaussians_upsampled_3", 96)):
+        assert ret[k].shape == (B, D * f, 13)
+    assert ret["gaussians"] is ret["gaussians_upsampled"] and "query_pcd_xyz" in ret
+    vs, ps, cs, tf = cameras(B * V)
+    c = {"cam_view": torch.tensor(vs, device=dev).reshape(B, V, 4, 4), "cam_view_proj": torch.tensor(ps, device=dev).reshape(B, V, 4, 4),
+         "cam_pos": torch.tensor(cs, device=dev).reshape(B, V, 3), "tanfov": torch.tensor(tf)}
+    bg = torch.tensor([0.0, 0.0, 0.0], device=dev)
+    out = ae(img=None, c=c, latent=ret, behaviour="triplane_dec", bg_color=bg, render_all_scale=True)
+    assert list(out) == ["gaussians_base", "gaussians_upsampled", "gaussians_upsampled_2", "gaussians_upsampled_3"]
+    rnd = GaussianRenderer2DGS(512, 3, {})
+    for key, size in SurfelAE.OUTPUT_SIZE.items():
+        r = out[key]
+        assert r["image"].shape == (B, V, 3, size, size) and r["image_depth"].shape == (B, V, 1, size, size)
+        ref = rnd.render(ret[key], c["cam_view"], c["cam_view_proj"], c["cam_pos"], tf, bg_color=bg, output_size=size)
+        assert torch.equal(r["image"], ref["image"]) and torch.equal(r["image_mask"], ref["alpha"])
+        assert torch.equal(r["image_raw"], ref["image"] * 2 - 1)
+    two = ae(latent=ret, c=c, behaviour="triplane_dec")             # rand_base_render: one random coarse level + the finest
+    assert len(two) == 2 and list(two)[-1] == "gaussians_upsampled_3"
+    full = ae(latent=lat, c=c, behaviour="decode_after_vae")
+    assert "gaussians_upsampled_3" in full
+    with pytest.raises(NotImplementedError):
+        ae(img=torch.zeros(1), behaviour="enc")
