@@ -44,6 +44,7 @@ class StandinRasterizer:
         p = lambda t: C.c_void_p(t.data_ptr())
         st = C.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)
         V, H, W, P = self.V, self.H, self.W, self.P
+        g13, vms, pms, bg = g13.contiguous().float(), vms.contiguous().float(), pms.contiguous().float(), bg.contiguous().float()
         color = torch.empty(V, 3, H, W, device=self.dev)
         allmap = torch.empty(V, 7, H, W, device=self.dev)
         radii = torch.empty(V, P, device=self.dev, dtype=torch.int32)
@@ -61,6 +62,7 @@ class StandinRasterizer:
         p = lambda t: C.c_void_p(t.data_ptr())
         st = C.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)
         g13, vms, pms, bg, mod = self._saved
+        d_color, d_allmap = d_color.contiguous().float(), d_allmap.contiguous().float()
         grad = torch.zeros(self.P, 13, device=self.dev)
         for v in range(self.V):
             rc = self.L.st_backward(C.c_void_p(self.ctx[v]), p(g13), p(vms[v]), p(pms[v]), p(bg), mod, p(d_color[v]), p(d_allmap[v]),

@@ -30,7 +30,9 @@ import numpy as np  # noqa: E402
 P_SURFELS, RES, VIEWS = 100000, 512, 6
 # kernels of libga_b200.so per device-timed step: preprocess, tile scan, scatter, 2 sort kernels, render fwd | render bwd,
 # preprocess bwd (+ 3 memsets, not counted)
-LAUNCHES_PER_STEP = 8
+# (round 2: + tile-area pre-pass, its scan, list-walking kernel A, recompute kernel A for flagged tiles, kernel B,
+# fused fallback kernel = 13 launches of our kernels per step)
+LAUNCHES_PER_STEP = 13
 METRIC = "512^2 views/sec @100k Gaussians (surfel raster fwd+bwd)"
 UNIT = "views/s"
 CONFIG = {"workload": "C2: 100k surfels, 512x512, 6 views, raster fwd+bwd",
@@ -216,7 +218,9 @@ def run_gpu(args):
     _, _, _, st = raster.forward_raw(g13, vm.view(B, V, 4, 4), pm.view(B, V, 4, 4), bg, H, W)
     D = st["num_rendered"]
     max_inst = int(D * 1.25) + 1024
-    L = raster.layout(B, P, V, H, W, max_inst)
+    LIST_K = raster.LIST_K                       # forward+backward workload: the forward records the per-pixel lists
+    lib.ga_raster_forward_ex.restype = C.c_int
+    L = raster.layout(B, P, V, H, W, max_inst, LIST_K)
     ws = torch.empty(L.total_bytes, device=dev, dtype=torch.uint8)
     color = torch.empty(B, V, 3, H, W, device=dev)
     allmap = torch.empty(B, V, 7, H, W, device=dev)
@@ -229,12 +233,12 @@ def run_gpu(args):
     p = lambda t: C.c_void_p(t.data_ptr())
 
     def step_device():
-        rc = lib.ga_raster_forward(p(g13), B, P, V, p(vm), p(pm), p(bg), H, W, 1.0, p(color), p(allmap),
-                                   p(radii), p(ws), L.total_bytes, max_inst, stream)
+        rc = lib.ga_raster_forward_ex(p(g13), B, P, V, p(vm), p(pm), p(bg), H, W, 1.0, p(color), p(allmap),
+                                      p(radii), p(ws), L.total_bytes, max_inst, LIST_K, None, None, stream)
         assert rc == 0, rc
-        rc = lib.ga_raster_backward(p(g13), B, P, V, p(vm), p(pm), p(bg), H, W, 1.0, p(radii), p(d_color),
-                                    p(d_allmap), p(ws), L.total_bytes, max_inst, p(scratch), nscr, p(grad),
-                                    stream)
+        rc = lib.ga_raster_backward_ex(p(g13), B, P, V, p(vm), p(pm), p(bg), H, W, 1.0, p(radii), p(d_color),
+                                       p(d_allmap), p(ws), L.total_bytes, max_inst, LIST_K, p(scratch), nscr, p(grad),
+                                       stream)
         assert rc == 0, rc
 
     def barrier():
@@ -393,6 +397,15 @@ def run_gpu(args):
             if key in tj:
                 traffic, traffic_src = tj[key]["dram_bytes"], tj.get("_source")
         step_bytes = V * (52.0 * P + 40.0 * HW) + 76.0 * D + V * (60.0 * HW + 104.0 * P) + 76.0 * D
+        # FP32-issue view of the forward composite: dense-equivalent pair evaluations = sum over tiles of
+        # (instances in the tile x 256 pixels), ~50 flop each, against 148 SMs x 128 lanes x 2 x 1.965 GHz
+        ts = ws[L.tile_start:L.tile_start + 4 * (V * ((H + 15) // 16) * ((W + 15) // 16) + 1)].view(torch.int32).cpu().numpy().astype(np.int64)
+        evals = float((ts[1:] - ts[:-1]).sum() * 256)
+        fp32_peak = 148 * 128 * 2 * 1.965e9 / 1e12
+        fp32 = {"kernel": "render_fwd", "dense_pair_evals": evals, "flop_per_eval": 50,
+                "achieved_tflops_dense_equivalent": evals * 50 / (stages["render_fwd"] * 1e-3) / 1e12, "peak_tflops": fp32_peak,
+                "frac_dense_equivalent": evals * 50 / (stages["render_fwd"] * 1e-3) / 1e12 / fp32_peak,
+                "note": "culling skips most of these pairs; the figure says how far the kernel is from brute force at FP32 peak"}
         cpu_v, cpu_n, cpu_dt = cpu_views_per_s(2, 10.0) if world == 1 else (None, 0, 0.0)
         dit_leg = None
         if world == 1 and not args.no_dit:
@@ -434,7 +447,8 @@ def run_gpu(args):
                "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": hbm, "unit": "GB/s",
                             "frac": achieved / hbm, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                             "algorithmic_bytes_per_launch": dom_bytes,
-                            "whole_step_algorithmic_GBs": step_bytes / (dev_ms_max / args.steps * 1e-3) / 1e9},
+                            "whole_step_algorithmic_GBs": step_bytes / (dev_ms_max / args.steps * 1e-3) / 1e9,
+                            "whole_step_frac": step_bytes / (dev_ms_max / args.steps * 1e-3) / 1e9 / hbm, "fp32": fp32},
                "cpu_baseline": ({"value": cpu_v, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
                                  "sample": "%d views fwd+bwd of the same 100k/512^2 scene in %.1f s "
                                            "(oracle/surfel_oracle.c, OpenMP)" % (cpu_n, cpu_dt)}

@@ -17,7 +17,7 @@ _lib = None
 class GaRasterLayout(C.Structure):
     _fields_ = [(n, C.c_size_t) for n in (
         "total_bytes", "status", "rec", "depth", "rect", "tile_count", "tile_start",
-        "keys", "ids", "final_T", "n_contrib", "inst_off", "inst_cnt")]
+        "keys", "ids", "final_T", "n_contrib", "inst_off", "inst_cnt", "n_list", "tile_flag", "tile_rec_start", "lists")]
 
 
 def lib():
@@ -34,6 +34,12 @@ def lib():
     vp, i32, i64, f32, sz = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_size_t
     L.ga_raster_layout.argtypes = [i32, i32, i32, i32, i32, i64, C.POINTER(GaRasterLayout)]
     L.ga_raster_layout.restype = i32
+    L.ga_raster_layout_ex.argtypes = [i32, i32, i32, i32, i32, i64, i32, C.POINTER(GaRasterLayout)]
+    L.ga_raster_layout_ex.restype = i32
+    L.ga_raster_forward_ex.argtypes = [vp, i32, i32, i32, vp, vp, vp, i32, i32, f32, vp, vp, vp, vp, sz, i64, i32, vp, vp, vp]
+    L.ga_raster_forward_ex.restype = i32
+    L.ga_raster_backward_ex.argtypes = [vp, i32, i32, i32, vp, vp, vp, i32, i32, f32, vp, vp, vp, vp, sz, i64, i32, vp, sz, vp, vp]
+    L.ga_raster_backward_ex.restype = i32
     L.ga_raster_forward.argtypes = [vp, i32, i32, i32, vp, vp, vp, i32, i32, f32,
                                     vp, vp, vp, vp, sz, i64, vp]
     L.ga_raster_forward.restype = i32

@@ -31,6 +31,23 @@ extern "C" int ga_profile_read(float *ms, int n)
     return 5;
 }
 
+// side stream + events for work that is independent of the main stream's next kernel (one set per device)
+GaSide *ga_side()
+{
+    static GaSide sides[64];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) return nullptr;
+    GaSide &g = sides[dev];
+    if (!g.st) {
+        if (cudaStreamCreateWithFlags(&g.st, cudaStreamNonBlocking) != cudaSuccess) { g.st = nullptr; return nullptr; }
+        cudaEventCreateWithFlags(&g.fork, cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&g.join, cudaEventDisableTiming);
+    }
+    return &g;
+}
+
+
 static int g_radius_formula = GA_RADIUS_FORMULA, g_quat_norm_grad = GA_QUAT_NORM_GRAD;
 
 extern "C" int ga_raster_set_variant(int radius_formula, int quat_norm_grad)
@@ -48,8 +65,10 @@ extern "C" int ga_raster_get_variant(int *radius_formula, int *quat_norm_grad)
 }
 
 static int make_dims(int batch, int P, int views, int H, int W, float scale_modifier,
-                     int64_t max_instances, RasterDims *d)
+                     int64_t max_instances, RasterDims *d, int list_k = 0)
 {
+    if (list_k < 0 || list_k > 1024) return GA_ERR_BADARG;
+    d->list_k = list_k;
     if (batch <= 0 || P <= 0 || views <= 0 || H <= 0 || W <= 0 || max_instances < 0) return GA_ERR_BADARG;
     d->batch = batch; d->P = P; d->views = views; d->NV = batch * views;
     d->H = H; d->W = W;
@@ -68,8 +87,14 @@ static int make_dims(int batch, int P, int views, int H, int W, float scale_modi
 extern "C" int ga_raster_layout(int batch, int P, int views, int H, int W,
                                 int64_t max_instances, GaRasterLayout *L)
 {
+    return ga_raster_layout_ex(batch, P, views, H, W, max_instances, 0, L);
+}
+
+extern "C" int ga_raster_layout_ex(int batch, int P, int views, int H, int W,
+                                   int64_t max_instances, int list_k, GaRasterLayout *L)
+{
     RasterDims d;
-    int rc = make_dims(batch, P, views, H, W, 1.0f, max_instances, &d);
+    int rc = make_dims(batch, P, views, H, W, 1.0f, max_instances, &d, list_k);
     if (rc) return rc;
     if (!L) return GA_ERR_BADARG;
     const size_t NVP = (size_t)d.NV * P, NVT = (size_t)d.NV * d.T, HW = (size_t)H * W;
@@ -87,6 +112,10 @@ extern "C" int ga_raster_layout(int batch, int P, int views, int H, int W,
     L->n_contrib = off;  off = align_up(off + (size_t)d.NV * 2 * HW * sizeof(int32_t), 256);
     L->inst_off = off;   off = align_up(off + mi * sizeof(uint32_t), 256);
     L->inst_cnt = off;   off = align_up(off + mi * sizeof(uint32_t), 256);
+    L->n_list = off;     off = align_up(off + (list_k ? (size_t)d.NV * HW * sizeof(int32_t) : 0), 256);
+    L->tile_flag = off;  off = align_up(off + (list_k ? NVT * sizeof(uint32_t) : 0), 256);
+    L->tile_rec_start = off; off = align_up(off + (list_k ? (NVT + 1) * sizeof(uint32_t) : 0), 256);
+    L->lists = off;      off = align_up(off + (size_t)list_k * NVT * 256 * 16, 256);
     L->total_bytes = off;
     return 0;
 }
@@ -106,6 +135,10 @@ static void carve(const GaRasterLayout &L, void *base, RasterWs *w)
     w->n_contrib = (int32_t *)(p + L.n_contrib);
     w->inst_off = (uint32_t *)(p + L.inst_off);
     w->inst_cnt = (uint32_t *)(p + L.inst_cnt);
+    w->n_list = (int32_t *)(p + L.n_list);
+    w->tile_flag = (uint32_t *)(p + L.tile_flag);
+    w->tile_rec_start = (uint32_t *)(p + L.tile_rec_start);
+    w->lists = (uint4 *)(p + L.lists);
 }
 
 static int raster_forward_impl(int stage, const float *gauss13, int batch, int P, int views,
@@ -113,15 +146,15 @@ static int raster_forward_impl(int stage, const float *gauss13, int batch, int P
                                int H, int W, float scale_modifier,
                                float *out_color, float *out_allmap, int32_t *out_radii,
                                void *workspace, size_t workspace_bytes, int64_t max_instances,
-                               void *stream, int32_t *status_host = nullptr, void *status_event = nullptr)
+                               void *stream, int32_t *status_host = nullptr, void *status_event = nullptr, int list_k = 0)
 {
     RasterDims d;
-    int rc = make_dims(batch, P, views, H, W, scale_modifier, max_instances, &d);
+    int rc = make_dims(batch, P, views, H, W, scale_modifier, max_instances, &d, list_k);
     if (rc) return rc;
     if (!gauss13 || !viewmats || !projmats || !bg || !out_color || !out_allmap || !out_radii || !workspace)
         return GA_ERR_BADARG;
     GaRasterLayout L;
-    ga_raster_layout(batch, P, views, H, W, max_instances, &L);
+    ga_raster_layout_ex(batch, P, views, H, W, max_instances, list_k, &L);
     if (workspace_bytes < L.total_bytes) return GA_ERR_WORKSPACE;
     RasterWs w;
     carve(L, workspace, &w);
@@ -137,7 +170,10 @@ static int raster_forward_impl(int stage, const float *gauss13, int batch, int P
         prof(2, s);
     }
     if (stage == 0 || stage == 2) {
-        if ((e = ga_launch_render_fwd(d, w, bg, out_color, out_allmap, s)) != cudaSuccess) return (int)e;
+        if (list_k && (e = cudaMemsetAsync(w.tile_flag, 0, (size_t)d.NV * d.T * sizeof(uint32_t), s)) != cudaSuccess) return (int)e;
+        if (list_k) e = ga_launch_render_fwd_with_slices(d, w, bg, out_color, out_allmap, s);
+        else e = ga_launch_render_fwd(d, w, bg, out_color, out_allmap, s);
+        if (e != cudaSuccess) return (int)e;
         prof(3, s);
     }
     return 0;
@@ -165,6 +201,19 @@ extern "C" int ga_raster_forward_async(const float *gauss13, int batch, int P, i
     return raster_forward_impl(0, gauss13, batch, P, views, viewmats, projmats, bg, H, W, scale_modifier, out_color,
                                out_allmap, out_radii, workspace, workspace_bytes, max_instances, stream, status_host,
                                status_event);
+}
+
+extern "C" int ga_raster_forward_ex(const float *gauss13, int batch, int P, int views,
+                                    const float *viewmats, const float *projmats, const float *bg,
+                                    int H, int W, float scale_modifier,
+                                    float *out_color, float *out_allmap, int32_t *out_radii,
+                                    void *workspace, size_t workspace_bytes, int64_t max_instances, int list_k,
+                                    int32_t *status_host, void *status_event, void *stream)
+{
+    if ((status_host == nullptr) != (status_event == nullptr)) return GA_ERR_BADARG;
+    return raster_forward_impl(0, gauss13, batch, P, views, viewmats, projmats, bg, H, W, scale_modifier, out_color,
+                               out_allmap, out_radii, workspace, workspace_bytes, max_instances, stream, status_host,
+                               status_event, list_k);
 }
 
 extern "C" int ga_raster_forward_bin(const float *gauss13, int batch, int P, int views,
@@ -215,14 +264,28 @@ extern "C" int ga_raster_backward(const float *gauss13, int batch, int P, int vi
                                   void *scratch, size_t scratch_bytes,
                                   float *grad_gauss13, void *stream)
 {
+    return ga_raster_backward_ex(gauss13, batch, P, views, viewmats, projmats, bg, H, W, scale_modifier, radii, dL_dcolor,
+                                 dL_dallmap, workspace, workspace_bytes, max_instances, 0, scratch, scratch_bytes,
+                                 grad_gauss13, stream);
+}
+
+extern "C" int ga_raster_backward_ex(const float *gauss13, int batch, int P, int views,
+                                     const float *viewmats, const float *projmats, const float *bg,
+                                     int H, int W, float scale_modifier,
+                                     const int32_t *radii,
+                                     const float *dL_dcolor, const float *dL_dallmap,
+                                     const void *workspace, size_t workspace_bytes, int64_t max_instances, int list_k,
+                                     void *scratch, size_t scratch_bytes,
+                                     float *grad_gauss13, void *stream)
+{
     RasterDims d;
-    int rc = make_dims(batch, P, views, H, W, scale_modifier, max_instances, &d);
+    int rc = make_dims(batch, P, views, H, W, scale_modifier, max_instances, &d, list_k);
     if (rc) return rc;
     if (!gauss13 || !viewmats || !projmats || !bg || !radii || !dL_dcolor || !dL_dallmap ||
         !workspace || !scratch || !grad_gauss13)
         return GA_ERR_BADARG;
     GaRasterLayout L;
-    ga_raster_layout(batch, P, views, H, W, max_instances, &L);
+    ga_raster_layout_ex(batch, P, views, H, W, max_instances, list_k, &L);
     if (workspace_bytes < L.total_bytes) return GA_ERR_WORKSPACE;
     const size_t need = bwd_acc_bytes(batch, P, views);                 // the accumulators are mandatory, the lists optional
     if (scratch_bytes < need) return GA_ERR_WORKSPACE;
@@ -240,7 +303,6 @@ extern "C" int ga_raster_backward(const float *gauss13, int batch, int P, int vi
         if (scratch_bytes > fixed + 4096) {
             char *p = (char *)scratch + need;
             lists.tile_rec_start = (uint32_t *)p;
-            lists.flag = (int32_t *)(p + bwd_tiles_bytes(batch, views));
             lists.records = (uint4 *)(p + bwd_tiles_bytes(batch, views) + 256);
             const size_t cap = (scratch_bytes - fixed) / 16;
             lists.capacity = (uint32_t)(cap > 0xfffffff0ull ? 0xfffffff0ull : cap);

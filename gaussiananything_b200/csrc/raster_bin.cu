@@ -278,8 +278,20 @@ cudaError_t ga_launch_binning(const RasterDims &d, const RasterWs &w, cudaStream
     }
     dim3 grid((d.P + 255) / 256, d.NV);
     scatter_kernel<<<grid, 256, 0, s>>>(d, w);
-    sort_tiles_warp_kernel<<<(d.NV * d.T + 7) / 8, 256, 0, s>>>(d, w);
     const int big_grid = d.NV * d.T < 148 * 7 ? d.NV * d.T : 148 * 7;      // 32 KB of keys per block: 7 blocks per SM
-    sort_tiles_kernel<<<big_grid, 256, 0, s>>>(d, w);
+    // the few tiles above the warp-sort limit are sorted by whole blocks (a long tail of a handful of CTAs): on the
+    // side stream, beside the warp-per-tile kernel that fills the GPU, instead of after it
+    GaSide *g = ga_side();
+    if (g) {
+        cudaEventRecord(g->fork, s);
+        cudaStreamWaitEvent(g->st, g->fork, 0);
+        sort_tiles_kernel<<<big_grid, 256, 0, g->st>>>(d, w);
+        cudaEventRecord(g->join, g->st);
+        sort_tiles_warp_kernel<<<(d.NV * d.T + 7) / 8, 256, 0, s>>>(d, w);
+        cudaStreamWaitEvent(s, g->join, 0);
+    } else {
+        sort_tiles_warp_kernel<<<(d.NV * d.T + 7) / 8, 256, 0, s>>>(d, w);
+        sort_tiles_kernel<<<big_grid, 256, 0, s>>>(d, w);
+    }
     return cudaGetLastError();
 }

@@ -28,6 +28,7 @@ struct RasterDims {
     int64_t max_instances;
     // the two unpinned judgement calls of the restatement, switchable so that pinning against
     // upstream is a flip of the defaults below; ga_raster_set_variant() overrides them at run time (tests)
+    int list_k;                // > 0: the forward records every pixel's contributions (<= list_k per pixel), see RasterWs.lists
     int radius_formula;        // 0: ceil(max(ex, ey, 3*FilterSize))   1: ceil(3*max(ex, ey, FilterSize))
     int quat_norm_grad;        // 0: quaternion vjp not chained through q/|q| (upstream)   1: chained
 };
@@ -49,18 +50,31 @@ struct RasterWs {
     uint32_t *ids;
     float *final_T;
     int32_t *n_contrib;
+    // per-pixel contribution lists written by the forward when list_k > 0 (the backward then neither culls nor
+    // re-evaluates pairs): entry k of pixel p of tile t at lists[(t * list_k + k) * 256 + p] = {list position, alpha
+    // bits, depth bits, 0}; n_list[pixel] = contributions of the pixel; tile_flag[t] = 1 when a pixel of the tile had
+    // more than list_k (that tile's backward recomputes instead)
+    uint4 *lists;
+    int32_t *n_list;
+    uint32_t *tile_flag;
+    uint32_t *tile_rec_start;  // (list_k > 0) [NV*T + 1] slice layout of the backward's record buffer, computed by the forward
     uint32_t *inst_off;        // backward (split path): start of every instance's record slice
     uint32_t *inst_cnt;        // ... and the number of records in it
 };
 
 // global-memory record lists of the split backward (carved from the backward scratch buffer)
 struct BwdLists {
-    uint32_t *tile_rec_start;  // [NV*T + 1] exclusive scan of the per-tile slice totals
-    int32_t *flag;             // [0] = 1: lists do not fit, fused kernel runs; [1] = records needed
+    uint32_t *tile_rec_start;  // [NV*T + 1] exclusive scan of the per-tile slice totals; [NV*T] = records needed
+                               // (> capacity: the split kernels exit and the fused kernel runs)
     uint4 *records;
     uint32_t capacity;         // records the buffer holds
     uint32_t *inst_off, *inst_cnt;
 };
+
+// a side stream + fork/join events per device for kernels that are independent of the main stream's next kernel
+// (few long CTAs that would otherwise serialise behind / in front of a grid-filling kernel); defined in raster_api.cu
+struct GaSide { cudaStream_t st = nullptr; cudaEvent_t fork = nullptr, join = nullptr; };
+GaSide *ga_side();
 
 // kernel launchers (defined in the .cu files, called from raster_api.cu)
 cudaError_t ga_launch_preprocess(const RasterDims &d, const RasterWs &w, const float *gauss13,
@@ -81,6 +95,11 @@ cudaError_t ga_launch_binning(const RasterDims &d, const RasterWs &w, cudaStream
                               cudaEvent_t status_event = nullptr);
 cudaError_t ga_launch_render_fwd(const RasterDims &d, const RasterWs &w, const float *bg,
                                  float *out_color, float *out_allmap, cudaStream_t s);
+cudaError_t ga_launch_render_fwd_with_slices(const RasterDims &d, const RasterWs &w, const float *bg, float *out_color,
+                                             float *out_allmap, cudaStream_t s);
+#ifndef GA_LIST_K
+#define GA_LIST_K 32               /* default per-pixel list capacity callers pass as list_k */
+#endif
 cudaError_t ga_launch_render_bwd(const RasterDims &d, const RasterWs &w, const float *bg,
                                  const float *dL_dcolor, const float *dL_dallmap,
                                  float *grad_acc, const BwdLists &lists, cudaStream_t s);

@@ -88,7 +88,12 @@ __device__ __forceinline__ bool eval_pair(const float4 a, const float4 b, const 
 // and chunk with GS = 32, 32 with GS = 16, 26 with GS = 8 (17.5 with one list per lane, but per-lane lists make every
 // load a 32-address gather: 0.208 vs 0.199 ms in round 1).  Measured: 209 / 181 / 176 us per 6-view launch.  Results do not depend on GS:
 // the per-pixel sequence of contributing surfels is the same.
-template <int GS>
+//
+// LISTS: the kernel also records, per pixel, every surfel that contributed -- {position in the tile list, alpha,
+// depth} -- into a tile-major array (entry k of the tile's 256 pixels is one contiguous 4 KB row, so a warp's store is
+// four full 128-byte lines).  The backward then walks exactly these entries: no cull tests, no pair re-evaluation for
+// pairs that do not contribute, and the contribution decisions are the forward's own bits.
+template <int GS, bool LISTS>
 __global__ void __launch_bounds__(256, 4)
 render_fwd_kernel(RasterDims d, RasterWs ws, const float *__restrict__ bg,
                   float *__restrict__ out_color, float *__restrict__ out_allmap)
@@ -97,11 +102,13 @@ render_fwd_kernel(RasterDims d, RasterWs ws, const float *__restrict__ bg,
     constexpr int GW = GS == 32 ? 8 : 4;                         // group block width / height in pixels
     constexpr int GH = GS == 8 ? 2 : 4;
     __shared__ float4 s_rec[7][CHUNK];
+    __shared__ uint32_t s_area;                                  // LISTS: sum of the clipped cull-box areas staged so far
     if (ws.status[1]) return;
     const int view = blockIdx.z;
     const int tile = blockIdx.y * d.gx + blockIdx.x;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int grp = lane / GS, gl = lane % GS;
+    if (LISTS && threadIdx.x == 0) s_area = 0;
     const int ox = blockIdx.x * GA_BLOCK_X, oy = blockIdx.y * GA_BLOCK_Y;
     const int wx0 = (warp & 1) * 8, wy0 = (warp >> 1) * 4;       // warp's 8x4 block, tile-local
     // group blocks tile the warp block: GS=16 -> 2 side by side (4x4); GS=8 -> 2x2 arrangement of 4x2 blocks
@@ -121,10 +128,14 @@ render_fwd_kernel(RasterDims d, RasterWs ws, const float *__restrict__ bg,
     float T = 1.0f, C0 = 0, C1 = 0, C2 = 0, N0 = 0, N1 = 0, N2 = 0;
     float Dacc = 0, M1 = 0, M2 = 0, dist = 0, median_depth = 0;
     int last_contributor = 0, median_contributor = -1;
+    int nl = 0;                                                    // LISTS: contributions of this pixel so far
+    uint4 *my_list = nullptr;
+    if (LISTS) my_list = ws.lists + ((size_t)view * d.T + tile) * (size_t)d.list_k * 256 + (lyi * 16 + lxi);
 
     for (int c0 = 0; c0 < total; c0 += CHUNK) {
         if (__syncthreads_count(done) == 256) break;
         const int cnt = min(CHUNK, total - c0);
+        uint32_t area = 0;
         if ((int)threadIdx.x < cnt) {
             const uint32_t id = ws.ids[start + c0 + threadIdx.x];
             const float4 *src = reinterpret_cast<const float4 *>(rec_base + (size_t)id * GA_REC_F);
@@ -143,6 +154,19 @@ render_fwd_kernel(RasterDims d, RasterWs ws, const float *__restrict__ bg,
             s_rec[4][threadIdx.x] = make_float4(bb.x - oxf, bb.y - oxf, bb.z - oyf, bb.w - oyf);
             s_rec[5][threadIdx.x] = nr;
             s_rec[6][threadIdx.x] = gb;
+            if (LISTS) {
+                // slice length of this instance in the backward's record buffer = pixels of its cull box inside the tile
+                // (same formula as clipped_box_area(): box and tile in absolute coordinates)
+                const float x0 = fmaxf(bb.x, oxf), x1 = fminf(bb.y, oxf + 15.f);
+                const float y0 = fmaxf(bb.z, oyf), y1 = fminf(bb.w, oyf + 15.f);
+                const int wx = max(0, (int)floorf(x1) - (int)ceilf(x0) + 1), wy = max(0, (int)floorf(y1) - (int)ceilf(y0) + 1);
+                area = (uint32_t)(wx * wy);
+            }
+        }
+        if (LISTS) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) area += __shfl_xor_sync(0xffffffffu, area, o);
+            if (lane == 0 && area) atomicAdd(&s_area, area);
         }
         __syncthreads();
         for (int g0 = 0; g0 < cnt; g0 += 32) {
@@ -200,11 +224,24 @@ render_fwd_kernel(RasterDims d, RasterWs ws, const float *__restrict__ bg,
                         C0 += nr.w * w; C1 += gb.x * w; C2 += gb.y * w;
                         T = test_T;
                         last_contributor = contributor;
+                        if (LISTS) {
+                            if (nl < d.list_k)
+                                my_list[(size_t)nl * 256] = make_uint4((uint32_t)(contributor - 1), __float_as_uint(alpha),
+                                                                       __float_as_uint(depth), 0u);
+                            nl++;
+                        }
                     }
                 }
             }
         }
         __syncthreads();
+    }
+    if (LISTS) {
+        if (inside) ws.n_list[(size_t)view * d.H * d.W + (size_t)pyi * d.W + pxi] = nl;
+        if (nl > d.list_k) ws.tile_flag[(size_t)view * d.T + tile] = 1u;      // this tile's backward recomputes
+        // every chunk the backward can reach (positions below the last contributor) has been staged here, so the sum
+        // covers its slices; bwd_scan_area_kernel turns the per-tile sums into offsets
+        if (threadIdx.x == 0) ws.tile_rec_start[(size_t)view * d.T + tile] = s_area;
     }
     if (inside) {
         const size_t HW = (size_t)d.H * d.W;
@@ -242,9 +279,15 @@ cudaError_t ga_launch_render_fwd(const RasterDims &d, const RasterWs &w, const f
         g_fwd_group = (v == 32 || v == 16 || v == 8) ? v : GA_FWD_GROUP_DEFAULT;
     }
     dim3 grid(d.gx, d.gy, d.NV);
-    if (g_fwd_group == 32) render_fwd_kernel<32><<<grid, 256, 0, s>>>(d, w, bg, out_color, out_allmap);
-    else if (g_fwd_group == 16) render_fwd_kernel<16><<<grid, 256, 0, s>>>(d, w, bg, out_color, out_allmap);
-    else render_fwd_kernel<8><<<grid, 256, 0, s>>>(d, w, bg, out_color, out_allmap);
+    if (d.list_k > 0) {
+        if (g_fwd_group == 32) render_fwd_kernel<32, true><<<grid, 256, 0, s>>>(d, w, bg, out_color, out_allmap);
+        else if (g_fwd_group == 16) render_fwd_kernel<16, true><<<grid, 256, 0, s>>>(d, w, bg, out_color, out_allmap);
+        else render_fwd_kernel<8, true><<<grid, 256, 0, s>>>(d, w, bg, out_color, out_allmap);
+    } else {
+        if (g_fwd_group == 32) render_fwd_kernel<32, false><<<grid, 256, 0, s>>>(d, w, bg, out_color, out_allmap);
+        else if (g_fwd_group == 16) render_fwd_kernel<16, false><<<grid, 256, 0, s>>>(d, w, bg, out_color, out_allmap);
+        else render_fwd_kernel<8, false><<<grid, 256, 0, s>>>(d, w, bg, out_color, out_allmap);
+    }
     return cudaGetLastError();
 }
 
@@ -272,10 +315,16 @@ cudaError_t ga_launch_render_fwd(const RasterDims &d, const RasterWs &w, const f
 #endif
 #define BWD_MAXG 128
 #ifndef BWD_A_CTAS
-#define BWD_A_CTAS 3                /* resident CTAs per SM kernel A is compiled for */
+#define BWD_A_CTAS 4                /* resident CTAs per SM kernel A is compiled for (64 registers, no spills) */
+#endif
+#ifndef BWD_B_UNROLL
+#define BWD_B_UNROLL 2              /* records per loop iteration and lane in kernel B */
+#endif
+#ifndef BWD_B_CTAS
+#define BWD_B_CTAS 3
 #endif
 #ifndef BWD_B_TPI
-#define BWD_B_TPI 4                 /* lanes per instance in kernel B */
+#define BWD_B_TPI 2                 /* lanes per instance in kernel B (2: 364 us, 4: 375 us, 8: 400+ us on C2) */
 #endif
 
 struct BwdSmem {
@@ -422,12 +471,12 @@ __device__ __forceinline__ void bwd_phase_b(BwdSmem &sm, const int *cnt, int g0,
 __global__ void __launch_bounds__(256, BWD_CTAS)
 render_bwd_kernel(RasterDims d, RasterWs ws, const float *__restrict__ bg,
                   const float *__restrict__ dL_dcolor, const float *__restrict__ dL_dallmap,
-                  float *__restrict__ grad_acc, const int32_t *__restrict__ split_flag)
+                  float *__restrict__ grad_acc, const uint32_t *__restrict__ split_total, uint32_t split_capacity)
 {
     extern __shared__ __align__(16) uint8_t bwd_smem_raw[];
     BwdSmem &sm = *reinterpret_cast<BwdSmem *>(bwd_smem_raw);
     if (ws.status[1]) return;
-    if (split_flag && split_flag[0] == 0) return;      // the split kernels (below) did the work
+    if (split_total && split_total[0] <= split_capacity) return;      // the split kernels (below) did the work
     const int view = blockIdx.z;
     const int tile = blockIdx.y * d.gx + blockIdx.x;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -622,7 +671,7 @@ __device__ __forceinline__ int clipped_box_area(const float4 bb, int ox, int oy)
 
 // one warp per tile: sum of the clipped cull-box areas of the tile's instances
 __global__ void __launch_bounds__(256)
-bwd_tile_area_kernel(RasterDims d, RasterWs ws, BwdLists L)
+bwd_tile_area_kernel(RasterDims d, RasterWs ws, uint32_t *__restrict__ tile_rec_start)
 {
     if (ws.status[1]) return;
     const size_t t = (size_t)blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -639,12 +688,12 @@ bwd_tile_area_kernel(RasterDims d, RasterWs ws, BwdLists L)
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    if (lane == 0) L.tile_rec_start[t] = sum;
+    if (lane == 0) tile_rec_start[t] = sum;
 }
 
 // exclusive scan of the tile totals (one block); sets the fallback flag when the buffer is too small
 __global__ void __launch_bounds__(1024)
-bwd_scan_area_kernel(RasterDims d, RasterWs ws, BwdLists L)
+bwd_scan_area_kernel(RasterDims d, RasterWs ws, uint32_t *__restrict__ tile_rec_start)
 {
     __shared__ uint32_t s_warp[32];
     __shared__ uint32_t s_carry;
@@ -655,7 +704,7 @@ bwd_scan_area_kernel(RasterDims d, RasterWs ws, BwdLists L)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int base = 0; base < n; base += 1024) {
         const int i = base + threadIdx.x;
-        const uint32_t v = i < n ? L.tile_rec_start[i] : 0u;
+        const uint32_t v = i < n ? tile_rec_start[i] : 0u;
         uint32_t x = v;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -676,16 +725,18 @@ bwd_scan_area_kernel(RasterDims d, RasterWs ws, BwdLists L)
         }
         __syncthreads();
         const uint32_t excl = s_carry + s_warp[warp] + x - v;
-        if (i < n) L.tile_rec_start[i] = excl;
+        if (i < n) tile_rec_start[i] = excl;
         __syncthreads();
         if (threadIdx.x == 1023) s_carry = excl + v;
         __syncthreads();
     }
-    if (threadIdx.x == 0) {
-        L.tile_rec_start[n] = s_carry;
-        L.flag[0] = (s_carry > L.capacity) ? 1 : 0;       // 1: lists do not fit -> the fused kernel runs instead
-        L.flag[1] = (int32_t)s_carry;
-    }
+    if (threadIdx.x == 0) tile_rec_start[n] = s_carry;     // total records needed; > capacity -> the fused kernel runs instead
+}
+
+// the record buffer of the split backward is too small for this launch: every split kernel exits, the fused one runs
+__device__ __forceinline__ bool bwd_lists_overflow(const RasterDims &d, const BwdLists &L)
+{
+    return L.tile_rec_start[d.NV * d.T] > L.capacity;
 }
 
 struct BwdASmem {
@@ -696,14 +747,23 @@ struct BwdASmem {
     int maxc;
 };
 
+// LISTS = true: the pairs come from the per-pixel contribution lists the forward recorded (RasterWs.lists): every lane
+// walks ITS pixel's entries back to front -- {list position, alpha, depth} -- so there is no cull test, no pair
+// evaluation and no wasted round on a surfel that does not reach alpha >= 1/255 at this pixel; alpha and depth are
+// the forward's own bits.  LISTS = false recomputes (tiles whose lists overflowed, or list_k == 0).
+template <bool LISTS>
 __global__ void __launch_bounds__(256, BWD_A_CTAS)
 render_bwd_a_kernel(RasterDims d, RasterWs ws, BwdLists L, const float *__restrict__ bg,
                     const float *__restrict__ dL_dcolor, const float *__restrict__ dL_dallmap)
 {
     __shared__ BwdASmem sm;
-    if (ws.status[1] || L.flag[0]) return;
+    if (ws.status[1] || bwd_lists_overflow(d, L)) return;
     const int view = blockIdx.z;
     const int tile = blockIdx.y * d.gx + blockIdx.x;
+    {
+        const bool listed = d.list_k > 0 && ws.tile_flag[(size_t)view * d.T + tile] == 0;
+        if (listed != LISTS) return;                   // block-uniform: the other instantiation handles this tile
+    }
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ox = blockIdx.x * GA_BLOCK_X, oy = blockIdx.y * GA_BLOCK_Y;
     const int lx0 = (warp & 1) * 8, ly0 = (warp >> 1) * 4;
@@ -742,6 +802,18 @@ render_bwd_a_kernel(RasterDims d, RasterWs ws, BwdLists L, const float *__restri
     const float final_A = 1 - T_final;
     const float bg_dot_dpixel = bg[0] * dpx0 + bg[1] * dpx1 + bg[2] * dpx2;
     float last_alpha = 0, v_last = 0, v_acc = 0, last_dL_dT = 0;        // one scalar suffix recurrence (see the fused kernel)
+    // LISTS: this pixel's entries, walked from the last contribution to the first; `e` is the entry about to be used
+    // (three entries are kept in flight: one entry's math is ~60 instructions, a list row comes from L2 / HBM)
+    const uint4 *my_list = nullptr;
+    int kk = -1;
+    uint4 e = make_uint4(0u, 0u, 0u, 0u), e1 = e, e2 = e;
+    if (LISTS) {
+        my_list = ws.lists + ((size_t)view * d.T + tile) * (size_t)d.list_k * 256 + pix_local;
+        kk = inside ? ws.n_list[(size_t)view * HW + pix] - 1 : -1;
+        if (kk >= 0) e = __ldg(my_list + (size_t)kk * 256);
+        if (kk >= 1) e1 = __ldg(my_list + (size_t)(kk - 1) * 256);
+        if (kk >= 2) e2 = __ldg(my_list + (size_t)(kk - 2) * 256);
+    }
 
     if (threadIdx.x == 0) sm.maxc = 0;
     __syncthreads();
@@ -785,35 +857,9 @@ render_bwd_a_kernel(RasterDims d, RasterWs ws, BwdLists L, const float *__restri
         if ((int)threadIdx.x < cnt) L.inst_off[start + (hi - 1 - threadIdx.x)] = tile_base + my_off;
         __syncthreads();
 
-        for (int sb = 0; sb < cnt; sb += 32) {
-            bool hit = false;
-            if (sb + lane < cnt) {
-                const float4 bb = sm.rec[4][sb + lane];
-                hit = !(bb.y < bx_lo || bb.x > bx_hi || bb.w < by_lo || bb.z > by_hi);
-            }
-            unsigned mask = __ballot_sync(0xffffffffu, hit);
-            unsigned mine = 0;
-            while (mask) {
-                const int b = __ffs(mask) - 1;
-                mask &= mask - 1;
-                const float4 bb = sm.rec[4][sb + b];
-                if (pfx >= bb.x && pfx <= bb.y && pfy >= bb.z && pfy <= bb.w && (hi - 1 - (sb + b)) < last_contributor)
-                    mine |= 1u << b;
-            }
-            if (!inside) mine = 0;
-            while (__any_sync(0xffffffffu, mine != 0)) {
-                const bool active = mine != 0;
-                const int bsel = active ? __ffs(mine) - 1 : 0;
-                mine &= mine - 1;
-                const int jj = sb + bsel;
-                const int contributor = hi - 1 - jj;       // 0-based list position
-                const float4 a = sm.rec[0][jj], b = sm.rec[1][jj], c = sm.rec[2][jj];
-                PixelGeom pg;
-                float k0, k1, k2, l0, l1, l2;
-                const bool ok = active && eval_pair(a, b, c, pfx, pfy, pg, k0, k1, k2, l0, l1, l2);
-                if (ok) {
+        // one (pixel, surfel) contribution: the compositing recurrences backwards + the 16-byte record for kernel B
+        auto contribute = [&](const int jj, const int contributor, const float alpha, const float c_d) {
                     const float4 nr = sm.rec[3][jj], gb = sm.rec[5][jj];
-                    const float alpha = pg.alpha, c_d = pg.depth;
                     const float inv1ma = fast_rcp(1.f - alpha);
                     T = T * inv1ma;
                     const float w = alpha * T;
@@ -838,8 +884,48 @@ render_bwd_a_kernel(RasterDims d, RasterWs ws, BwdLists L, const float *__restri
                     const int slot = atomicAdd(&sm.cnt[jj], 1);          // < the instance's clipped box area by construction
                     L.records[(size_t)tile_base + sm.off[jj] + (uint32_t)slot] =
                         make_uint4((uint32_t)pix_local, __float_as_uint(dL_dalpha), __float_as_uint(dL_dz), __float_as_uint(w));
+        };
+        if (LISTS) {
+            while (true) {
+                const bool active = kk >= 0 && (int)e.x >= lo;      // entries are in descending list position
+                if (!__any_sync(0xffffffffu, active)) break;
+                if (active) {
+                    const uint4 cur = e;
+                    e = e1; e1 = e2;
+                    if (kk >= 3) e2 = __ldg(my_list + (size_t)(kk - 3) * 256);   // entries kk-1, kk-2, kk-3 are in flight
+                    kk--;
+                    contribute(hi - 1 - (int)cur.x, (int)cur.x, __uint_as_float(cur.y), __uint_as_float(cur.z));
                 }
             }
+        } else {
+        for (int sb = 0; sb < cnt; sb += 32) {
+            bool hit = false;
+            if (sb + lane < cnt) {
+                const float4 bb = sm.rec[4][sb + lane];
+                hit = !(bb.y < bx_lo || bb.x > bx_hi || bb.w < by_lo || bb.z > by_hi);
+            }
+            unsigned mask = __ballot_sync(0xffffffffu, hit);
+            unsigned mine = 0;
+            while (mask) {
+                const int b = __ffs(mask) - 1;
+                mask &= mask - 1;
+                const float4 bb = sm.rec[4][sb + b];
+                if (pfx >= bb.x && pfx <= bb.y && pfy >= bb.z && pfy <= bb.w && (hi - 1 - (sb + b)) < last_contributor)
+                    mine |= 1u << b;
+            }
+            if (!inside) mine = 0;
+            while (__any_sync(0xffffffffu, mine != 0)) {
+                const bool active = mine != 0;
+                const int bsel = active ? __ffs(mine) - 1 : 0;
+                mine &= mine - 1;
+                const int jj = sb + bsel;
+                const float4 a = sm.rec[0][jj], b = sm.rec[1][jj], c = sm.rec[2][jj];
+                PixelGeom pg;
+                float k0, k1, k2, l0, l1, l2;
+                const bool ok = active && eval_pair(a, b, c, pfx, pfy, pg, k0, k1, k2, l0, l1, l2);
+                if (ok) contribute(jj, hi - 1 - jj, pg.alpha, pg.depth);
+            }
+        }
         }
         __syncthreads();
         if ((int)threadIdx.x < cnt) L.inst_cnt[start + (hi - 1 - threadIdx.x)] = (uint32_t)sm.cnt[threadIdx.x];
@@ -850,14 +936,17 @@ render_bwd_a_kernel(RasterDims d, RasterWs ws, BwdLists L, const float *__restri
 }
 
 template <int TPI>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, BWD_B_CTAS)
 render_bwd_b_kernel(RasterDims d, RasterWs ws, BwdLists L, const float *__restrict__ dL_dcolor,
-                    const float *__restrict__ dL_dallmap, float *__restrict__ grad_acc)
+                    const float *__restrict__ dL_dallmap, float *__restrict__ grad_acc, const int tile_filter)
 {
     __shared__ float4 s_up[2][256];
-    if (ws.status[1] || L.flag[0]) return;
+    if (ws.status[1] || bwd_lists_overflow(d, L)) return;
     const int view = blockIdx.z;
     const int tile = blockIdx.y * d.gx + blockIdx.x;
+    // tile_filter 1: only tiles whose records came from the list-walking kernel A; 2: only the flagged (recomputed)
+    // ones -- the two chains A<true> -> B(1) and A<false> -> B(2) run on two streams; 0: every tile
+    if (tile_filter && (ws.tile_flag[(size_t)view * d.T + tile] != 0) != (tile_filter == 2)) return;
     const int ox = blockIdx.x * GA_BLOCK_X, oy = blockIdx.y * GA_BLOCK_Y;
     const size_t gt = (size_t)view * d.T + tile;
     const uint32_t start = ws.tile_start[gt], end = ws.tile_start[gt + 1];
@@ -883,9 +972,49 @@ render_bwd_b_kernel(RasterDims d, RasterWs ws, BwdLists L, const float *__restri
     const int lane = threadIdx.x & 31;
     const int sub = threadIdx.x % TPI;
     constexpr int IPB = 256 / TPI;              // instances per pass
-    for (int base = 0; base < total; base += IPB) {
-        const int inst = base + threadIdx.x / TPI;
-        const bool valid = inst < total;
+    // Instances carry 0 .. ~30 records; a warp's pass lasts as long as its longest instance.  So the tile's instances
+    // are handled in super-chunks of 512: a counting sort by record count (descending, empty ones dropped) decides
+    // which instance each lane group takes, and every warp gets instances of similar length.
+    __shared__ int s_bin[64];
+    __shared__ uint16_t s_perm[512];
+    __shared__ int s_m;
+    for (int c0 = 0; c0 < total; c0 += 512) {
+        const int cn = min(512, total - c0);
+        if (threadIdx.x < 64) s_bin[threadIdx.x] = 0;
+        __syncthreads();
+        int myn[2];
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const int i = h * 256 + threadIdx.x;
+            myn[h] = i < cn ? (int)L.inst_cnt[start + c0 + i] : 0;
+            if (myn[h] > 0) atomicAdd(&s_bin[min(myn[h], 63)], 1);
+        }
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            // exclusive prefix over the bins in DESCENDING count order (bin 63 first); bin 0 is unused
+            const int hi_bin = 63 - 2 * threadIdx.x, lo_bin = hi_bin - 1;
+            const int vh = s_bin[hi_bin], vl = lo_bin >= 1 ? s_bin[lo_bin] : 0;
+            int x = vh + vl;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int y = __shfl_up_sync(0xffffffffu, x, o);
+                if ((int)threadIdx.x >= o) x += y;
+            }
+            const int excl = x - (vh + vl);
+            s_bin[hi_bin] = excl;
+            if (lo_bin >= 1) s_bin[lo_bin] = excl + vh;
+            if (threadIdx.x == 31) s_m = x;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int h = 0; h < 2; h++)
+            if (myn[h] > 0) s_perm[atomicAdd(&s_bin[min(myn[h], 63)], 1)] = (uint16_t)(h * 256 + threadIdx.x);
+        __syncthreads();
+        const int m = s_m;
+    for (int base = 0; base < m; base += IPB) {
+        const int slot = base + threadIdx.x / TPI;
+        const bool valid = slot < m;
+        const int inst = valid ? c0 + (int)s_perm[slot] : 0;
         const int n = valid ? (int)L.inst_cnt[start + inst] : 0;
         float g[GA_GRAD_F];
 #pragma unroll
@@ -897,8 +1026,7 @@ render_bwd_b_kernel(RasterDims d, RasterWs ws, BwdLists L, const float *__restri
             const float4 a = __ldg(src), b = __ldg(src + 1), c = __ldg(src + 2);
             const float opa = c.w;
             const uint4 *lst = L.records + L.inst_off[start + inst];
-            for (int r = sub; r < n; r += TPI) {
-                const uint4 rc = lst[r];
+            auto process = [&](const uint4 rc) {
                 const int pix = (int)rc.x;
                 const float dL_dalpha = __uint_as_float(rc.y), dL_dz = __uint_as_float(rc.z), w = __uint_as_float(rc.w);
                 const float pfx = (float)(ox + (pix & 15)), pfy = (float)(oy + (pix >> 4));
@@ -929,20 +1057,64 @@ render_bwd_b_kernel(RasterDims d, RasterWs ws, BwdLists L, const float *__restri
                 const float4 ua = s_up[0][pix], ub = s_up[1][pix];
                 g[15] += w * ua.x; g[16] += w * ua.y; g[17] += w * ua.z;
                 g[11] += w * ua.w; g[12] += w * ub.x; g[13] += w * ub.y;
+            };
+#if BWD_B_UNROLL == 2
+            // two records per iteration: two independent dependency chains per lane (the kernel is latency bound)
+            uint4 n0 = sub < n ? __ldg(lst + sub) : make_uint4(0u, 0u, 0u, 0u);
+            uint4 n1 = sub + TPI < n ? __ldg(lst + sub + TPI) : n0;
+            for (int r = sub; r < n; r += 2 * TPI) {
+                const uint4 r0 = n0;
+                // no second record: reuse the first one's pixel with zero upstream terms (adds exact zeros), so both
+                // bodies run unconditionally and the compiler can interleave them
+                const uint4 r1 = (r + TPI < n) ? n1 : make_uint4(n0.x, 0u, 0u, 0u);
+                if (r + 2 * TPI < n) n0 = __ldg(lst + r + 2 * TPI);
+                if (r + 3 * TPI < n) n1 = __ldg(lst + r + 3 * TPI);
+                process(r0);
+                process(r1);
             }
+#else
+            uint4 nxt = sub < n ? __ldg(lst + sub) : make_uint4(0u, 0u, 0u, 0u);
+            for (int r = sub; r < n; r += TPI) {
+                const uint4 rc = nxt;
+                if (r + TPI < n) nxt = __ldg(lst + r + TPI);           // the next record's load overlaps this one's math
+                process(rc);
+            }
+#endif
         }
         if (__any_sync(0xffffffffu, n > 0)) {
             float *dst = acc_base + (size_t)id * GA_GRAD_F;          // lanes without records carry zeros (id 0, adds skipped)
             reduce_scatter18<TPI>(g, lane, dst);
         }
     }
+        __syncthreads();                         // s_bin / s_perm are rebuilt for the next super-chunk
+    }
 }
 
 static int g_bwd_split = -1;
 
+// slice layout of the split backward's record buffer: per-tile sums of the clipped cull-box areas + their scan.
+// Called by the forward (list_k > 0) on a side stream, concurrently with the composite, or by the backward.
+cudaError_t ga_launch_bwd_slices(const RasterDims &d, const RasterWs &w, uint32_t *tile_rec_start, cudaStream_t s)
+{
+    const int tiles = d.NV * d.T;
+    bwd_tile_area_kernel<<<(tiles + 7) / 8, 256, 0, s>>>(d, w, tile_rec_start);
+    bwd_scan_area_kernel<<<1, 1024, 0, s>>>(d, w, tile_rec_start);
+    return cudaGetLastError();
+}
+
+cudaError_t ga_launch_render_fwd_with_slices(const RasterDims &d, const RasterWs &w, const float *bg, float *out_color,
+                                             float *out_allmap, cudaStream_t s)
+{
+    // the LISTS forward kernel leaves every tile's slice total in tile_rec_start; one small block turns them into offsets
+    cudaError_t e = ga_launch_render_fwd(d, w, bg, out_color, out_allmap, s);
+    if (e != cudaSuccess) return e;
+    bwd_scan_area_kernel<<<1, 1024, 0, s>>>(d, w, w.tile_rec_start);
+    return cudaGetLastError();
+}
+
 cudaError_t ga_launch_render_bwd(const RasterDims &d, const RasterWs &w, const float *bg,
                                  const float *dL_dcolor, const float *dL_dallmap,
-                                 float *grad_acc, const BwdLists &lists, cudaStream_t s)
+                                 float *grad_acc, const BwdLists &lists_in, cudaStream_t s)
 {
     static GaPerDevice attr_set;
     if (ga_first_use_on_device(attr_set)) {
@@ -955,16 +1127,42 @@ cudaError_t ga_launch_render_bwd(const RasterDims &d, const RasterWs &w, const f
         g_bwd_split = (e && e[0] == '0') ? 0 : 1;
     }
     dim3 grid(d.gx, d.gy, d.NV);
+    BwdLists lists = lists_in;
     const bool split = g_bwd_split && lists.records && lists.capacity > 0;
     if (split) {
-        const int tiles = d.NV * d.T;
-        bwd_tile_area_kernel<<<(tiles + 7) / 8, 256, 0, s>>>(d, w, lists);
-        bwd_scan_area_kernel<<<1, 1024, 0, s>>>(d, w, lists);
-        render_bwd_a_kernel<<<grid, 256, 0, s>>>(d, w, lists, bg, dL_dcolor, dL_dallmap);
-        render_bwd_b_kernel<BWD_B_TPI><<<grid, 256, 0, s>>>(d, w, lists, dL_dcolor, dL_dallmap, grad_acc);
+        cudaError_t e;
+        if (d.list_k > 0) {
+            lists.tile_rec_start = w.tile_rec_start;                 // laid out by the forward
+        } else if ((e = ga_launch_bwd_slices(d, w, lists.tile_rec_start, s)) != cudaSuccess) {
+            return e;
+        }
+        if (d.list_k > 0) {
+            // tiles whose per-pixel lists overflowed are few and long: their recompute kernel runs beside the
+            // list-walking one instead of after it
+            // tiles whose per-pixel lists overflowed are few and long: their chain (recompute kernel A -> kernel B on
+            // those tiles) runs on the side stream beside the list-walking chain instead of in front of / behind it
+            GaSide *g = ga_side();
+            if (g) {
+                cudaEventRecord(g->fork, s);
+                cudaStreamWaitEvent(g->st, g->fork, 0);
+                render_bwd_a_kernel<false><<<grid, 256, 0, g->st>>>(d, w, lists, bg, dL_dcolor, dL_dallmap);
+                render_bwd_b_kernel<BWD_B_TPI><<<grid, 256, 0, g->st>>>(d, w, lists, dL_dcolor, dL_dallmap, grad_acc, 2);
+                cudaEventRecord(g->join, g->st);
+                render_bwd_a_kernel<true><<<grid, 256, 0, s>>>(d, w, lists, bg, dL_dcolor, dL_dallmap);
+                render_bwd_b_kernel<BWD_B_TPI><<<grid, 256, 0, s>>>(d, w, lists, dL_dcolor, dL_dallmap, grad_acc, 1);
+                cudaStreamWaitEvent(s, g->join, 0);
+            } else {
+                render_bwd_a_kernel<true><<<grid, 256, 0, s>>>(d, w, lists, bg, dL_dcolor, dL_dallmap);
+                render_bwd_a_kernel<false><<<grid, 256, 0, s>>>(d, w, lists, bg, dL_dcolor, dL_dallmap);
+                render_bwd_b_kernel<BWD_B_TPI><<<grid, 256, 0, s>>>(d, w, lists, dL_dcolor, dL_dallmap, grad_acc, 0);
+            }
+        } else {
+            render_bwd_a_kernel<false><<<grid, 256, 0, s>>>(d, w, lists, bg, dL_dcolor, dL_dallmap);
+            render_bwd_b_kernel<BWD_B_TPI><<<grid, 256, 0, s>>>(d, w, lists, dL_dcolor, dL_dallmap, grad_acc, 0);
+        }
     }
-    // fused kernel: the whole job when the split path is off, a no-op (flag == 0) or the fallback (flag == 1) otherwise
+    // fused kernel: the whole job when the split path is off, a no-op or the fallback (record buffer too small) otherwise
     render_bwd_kernel<<<grid, 256, sizeof(BwdSmem), s>>>(d, w, bg, dL_dcolor, dL_dallmap, grad_acc,
-                                                         split ? lists.flag : nullptr);
+                                                         split ? lists.tile_rec_start + d.NV * d.T : nullptr, lists.capacity);
     return cudaGetLastError();
 }

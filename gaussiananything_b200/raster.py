@@ -22,10 +22,13 @@ def _stream(dev):
     return C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
 
 
-def layout(batch, P, views, H, W, max_instances):
+LIST_K = 32          # per-pixel contribution-list capacity used when the caller will ask for gradients
+
+
+def layout(batch, P, views, H, W, max_instances, list_k=0):
     L = _lib.GaRasterLayout()
-    _lib.check(_lib.lib().ga_raster_layout(batch, P, views, H, W, max_instances, C.byref(L)),
-               "ga_raster_layout")
+    _lib.check(_lib.lib().ga_raster_layout_ex(batch, P, views, H, W, max_instances, int(list_k), C.byref(L)),
+               "ga_raster_layout_ex")
     return L
 
 
@@ -66,9 +69,12 @@ def _status_slot(dev):
     return slot
 
 
-def forward_raw(gauss13, viewmats, projmats, bg, H, W, scale_modifier=1.0, max_instances=None):
+def forward_raw(gauss13, viewmats, projmats, bg, H, W, scale_modifier=1.0, max_instances=None, list_k=None):
     """gauss13 [B,P,13], viewmats/projmats [B,V,4,4] (reference layout), bg [3].
-    Returns (color [B,V,3,H,W], allmap [B,V,7,H,W], radii [B,V,P], state)."""
+    Returns (color [B,V,3,H,W], allmap [B,V,7,H,W], radii [B,V,P], state).
+    list_k: per-pixel contribution lists for the backward (default: LIST_K when gauss13 requires grad, else 0)."""
+    if list_k is None:
+        list_k = LIST_K if gauss13.requires_grad else 0
     lib = _lib.lib()
     if not gauss13.is_cuda:
         raise RuntimeError("gaussiananything_b200 rasteriser needs CUDA tensors (no CPU fallback)")
@@ -81,10 +87,11 @@ def forward_raw(gauss13, viewmats, projmats, bg, H, W, scale_modifier=1.0, max_i
     projmats = projmats.reshape(B * V, 16).contiguous().float()
     bg = bg.to(device=dev, dtype=torch.float32).contiguous()
     with torch.cuda.device(dev):           # launches go to the tensors' device, not the process's current one
-        return _forward_on_device(lib, dev, gauss13, viewmats, projmats, bg, B, P, V, H, W, scale_modifier, max_instances)
+        return _forward_on_device(lib, dev, gauss13, viewmats, projmats, bg, B, P, V, H, W, scale_modifier, max_instances,
+                                  int(list_k))
 
 
-def _forward_on_device(lib, dev, gauss13, viewmats, projmats, bg, B, P, V, H, W, scale_modifier, max_instances):
+def _forward_on_device(lib, dev, gauss13, viewmats, projmats, bg, B, P, V, H, W, scale_modifier, max_instances, list_k):
     key = (B, P, V, H, W)
     if max_instances is None:
         max_instances = _capacity_hint.get(key, 4 * B * V * P + 1024)
@@ -93,23 +100,23 @@ def _forward_on_device(lib, dev, gauss13, viewmats, projmats, bg, B, P, V, H, W,
     radii = torch.empty(B, V, P, device=dev, dtype=torch.int32)
     host_status, ev = _status_slot(dev)
     while True:
-        L = layout(B, P, V, H, W, max_instances)
+        L = layout(B, P, V, H, W, max_instances, list_k)
         ws = torch.empty(L.total_bytes, device=dev, dtype=torch.uint8)
         # the whole forward is enqueued in one call; the instance count / overflow flag (where upstream reads
         # num_rendered back) is copied to pinned memory right after the tile scan, so this wait returns while the
         # GPU is still scattering, sorting and compositing -- no bubble in the stream
-        _lib.check(lib.ga_raster_forward_async(
+        _lib.check(lib.ga_raster_forward_ex(
             _ptr(gauss13), B, P, V, _ptr(viewmats), _ptr(projmats), _ptr(bg), H, W, float(scale_modifier),
-            _ptr(color), _ptr(allmap), _ptr(radii), _ptr(ws), L.total_bytes, max_instances,
+            _ptr(color), _ptr(allmap), _ptr(radii), _ptr(ws), L.total_bytes, max_instances, list_k,
             C.c_void_p(host_status.data_ptr()), C.c_void_p(ev.cuda_event), _stream(dev)),
-            "ga_raster_forward_async")
+            "ga_raster_forward_ex")
         ev.synchronize()
         status = host_status.clone()
         if int(status[1]) == 0:
             break
         max_instances = int(int(status[0]) * 1.25) + 1024
         _capacity_hint[key] = max_instances
-    state = dict(ws=ws, L=L, max_instances=max_instances, num_rendered=int(status[0]),
+    state = dict(ws=ws, L=L, max_instances=max_instances, num_rendered=int(status[0]), list_k=list_k,
                  gauss13=gauss13, viewmats=viewmats, projmats=projmats, bg=bg,
                  dims=(B, P, V, H, W), scale_modifier=float(scale_modifier), radii=radii)
     return color, allmap, radii, state
@@ -125,11 +132,11 @@ def backward_raw(state, grad_color, grad_allmap):
     with torch.cuda.device(dev):
         scratch = torch.empty(nbytes, device=dev, dtype=torch.uint8)
         grad = torch.empty(B, P, 13, device=dev, dtype=torch.float32)
-        rc = lib.ga_raster_backward(_ptr(state["gauss13"]), B, P, V, _ptr(state["viewmats"]),
+        rc = lib.ga_raster_backward_ex(_ptr(state["gauss13"]), B, P, V, _ptr(state["viewmats"]),
                                     _ptr(state["projmats"]), _ptr(state["bg"]), H, W,
                                     state["scale_modifier"], _ptr(state["radii"]),
                                     _ptr(grad_color), _ptr(grad_allmap),
-                                    _ptr(state["ws"]), state["L"].total_bytes, state["max_instances"],
+                                    _ptr(state["ws"]), state["L"].total_bytes, state["max_instances"], state.get("list_k", 0),
                                     _ptr(scratch), nbytes, _ptr(grad), _stream(dev))
     _lib.check(rc, "ga_raster_backward")
     return grad
@@ -138,7 +145,8 @@ def backward_raw(state, grad_color, grad_allmap):
 class _RasterizeSurfelsBatched(torch.autograd.Function):
     @staticmethod
     def forward(ctx, gauss13, viewmats, projmats, bg, H, W, scale_modifier):
-        color, allmap, radii, state = forward_raw(gauss13, viewmats, projmats, bg, H, W, scale_modifier)
+        color, allmap, radii, state = forward_raw(gauss13, viewmats, projmats, bg, H, W, scale_modifier,
+                                                  list_k=LIST_K if ctx.needs_input_grad[0] else 0)
         # the tensors the backward re-reads go through save_for_backward, so an in-place change between forward
         # and backward is detected by autograd's version check instead of silently giving wrong gradients
         ctx.save_for_backward(state.pop("gauss13"), state.pop("viewmats"), state.pop("projmats"))

@@ -50,6 +50,10 @@ typedef struct GaRasterLayout {
     size_t n_contrib;   /* int32[NV][2][H*W]  last contributor, median contributor */
     size_t inst_off;    /* uint32[max_instances]  backward: start of the instance's record slice */
     size_t inst_cnt;    /* uint32[max_instances]  backward: records in it */
+    size_t n_list;      /* int32[NV][H*W]         (list_k > 0) contributions recorded per pixel */
+    size_t tile_flag;   /* uint32[NV*T]           (list_k > 0) 1: a pixel of the tile had more than list_k */
+    size_t tile_rec_start; /* uint32[NV*T+1]      (list_k > 0) slice layout of the backward's record buffer */
+    size_t lists;       /* uint4[NV*T][list_k][256] (list_k > 0) {list position, alpha bits, depth bits, 0} */
 } GaRasterLayout;
 
 /* Fills *layout for NV = batch*views images of H x W, P surfels per batch item
@@ -57,6 +61,11 @@ typedef struct GaRasterLayout {
  * Host-only, no CUDA call. */
 int ga_raster_layout(int batch, int P, int views, int H, int W,
                      int64_t max_instances, GaRasterLayout *layout);
+
+/* As ga_raster_layout, with room for the per-pixel contribution lists the forward records when list_k > 0
+ * (list_k * 4 KB per tile; 32 is the default the Python mirror uses for calls that need gradients). */
+int ga_raster_layout_ex(int batch, int P, int views, int H, int W,
+                        int64_t max_instances, int list_k, GaRasterLayout *layout);
 
 /*
  * Forward.  gauss13: [batch][P][13] = xyz3 opacity1 scale2 quat4(wxyz) rgb3, the
@@ -75,6 +84,18 @@ int ga_raster_forward(const float *gauss13, int batch, int P, int views,
                       float *out_color, float *out_allmap, int32_t *out_radii,
                       void *workspace, size_t workspace_bytes, int64_t max_instances,
                       void *stream);
+
+/* ga_raster_forward with per-pixel contribution lists: list_k > 0 makes the composite record, for every pixel, the
+ * (list position, alpha, depth) of each surfel that contributed (up to list_k per pixel; a tile with a longer pixel
+ * is flagged and its backward recomputes).  ga_raster_backward_ex with the same list_k then walks those lists instead
+ * of re-culling and re-evaluating every (pixel, surfel) pair -- what upstream's backward.cu renderCUDA does.
+ * status_host / status_event: both NULL, or as in ga_raster_forward_async. */
+int ga_raster_forward_ex(const float *gauss13, int batch, int P, int views,
+                         const float *viewmats, const float *projmats, const float *bg,
+                         int H, int W, float scale_modifier,
+                         float *out_color, float *out_allmap, int32_t *out_radii,
+                         void *workspace, size_t workspace_bytes, int64_t max_instances, int list_k,
+                         int32_t *status_host, void *status_event, void *stream);
 
 /* The same forward in two halves, for callers that want to look at status[0..1] (instance count, overflow) after
  * the binning -- the point where upstream reads `num_rendered` back (rasterizer_impl.cu) -- and only then enqueue
@@ -101,6 +122,16 @@ int ga_raster_forward_async(const float *gauss13, int batch, int P, int views,
                             float *out_color, float *out_allmap, int32_t *out_radii,
                             void *workspace, size_t workspace_bytes, int64_t max_instances,
                             int32_t *status_host, void *status_event, void *stream);
+
+/* ga_raster_backward for a workspace laid out and filled with list_k (ga_raster_layout_ex / ga_raster_forward_ex). */
+int ga_raster_backward_ex(const float *gauss13, int batch, int P, int views,
+                          const float *viewmats, const float *projmats, const float *bg,
+                          int H, int W, float scale_modifier,
+                          const int32_t *radii,
+                          const float *dL_dcolor, const float *dL_dallmap,
+                          const void *workspace, size_t workspace_bytes, int64_t max_instances, int list_k,
+                          void *scratch, size_t scratch_bytes,
+                          float *grad_gauss13, void *stream);
 
 /* Post-processing of /root/reference/nsr/gs_surfel.py:121-163 for all views at once: image = clamp(color,0,1),
  * alpha = allmap[1], depth = nan_to_num(allmap[5], 0, 0), normal[d] = sum_c allmap[2+c] * view[d][c], dist = allmap[6].

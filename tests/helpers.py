@@ -18,7 +18,8 @@ def cameras(n, start=0):
         pose = so.orbit_pose25(30.0 + 47.0 * (k + start), 20.0 + 11.0 * ((k + start) % 4) - 15.0)
         v, p, c, tf = so.camera_from_pose25(pose)
         vs.append(v); ps.append(p); cs.append(c)
-    return np.stack(vs), np.stack(ps), np.stack(cs), tf
+    # camera_from_pose25 returns transposed VIEWS (Fortran order); hand out C-contiguous arrays
+    return (np.ascontiguousarray(np.stack(vs)), np.ascontiguousarray(np.stack(ps)), np.ascontiguousarray(np.stack(cs)), tf)
 
 
 def scene(P, seed, scale_boost=1.0, smin=None, smax=None):

@@ -537,3 +537,40 @@ def test_forward_lane_groups_are_bit_identical():
         assert lib.ga_raster_set_tuning(7) != 0
     finally:
         lib.ga_raster_set_tuning(8)
+
+
+@pytest.mark.parametrize("list_k", [32, 3])
+def test_backward_from_recorded_lists_matches_recompute_and_oracle(list_k):
+    """list_k > 0: the forward records every pixel's contributions and the backward walks them (no culling, no pair
+    re-evaluation).  list_k = 3 overflows in most tiles, which must then take the recompute path: the gradient is
+    the same either way (the list path reuses the forward's alpha bits, so not bit-identical) and matches the oracle."""
+    from gaussiananything_b200 import raster
+    P, H, W, V = 5000, 128, 112, 2
+    g = scene(P, 80, 5.0)
+    vs, ps, _, _ = cameras(V, start=4)
+    bg = [1.0, 0.5, 0.2]
+    dev = torch.device("cuda:0")
+    g13 = torch.tensor(g, device=dev)[None]
+    vm, pm = torch.tensor(vs, device=dev)[None], torch.tensor(ps, device=dev)[None]
+    rng = np.random.default_rng(2)
+    gc = rng.standard_normal((V, 3, H, W)).astype(np.float32)
+    ga = rng.standard_normal((V, 7, H, W)).astype(np.float32)
+    dgc, dga = torch.tensor(gc, device=dev)[None], torch.tensor(ga, device=dev)[None]
+    c0, a0, r0, s0 = raster.forward_raw(g13, vm, pm, torch.tensor(bg, device=dev), H, W, list_k=0)
+    g0 = raster.backward_raw(s0, dgc, dga)[0].cpu().numpy()
+    c1, a1, r1, s1 = raster.forward_raw(g13, vm, pm, torch.tensor(bg, device=dev), H, W, list_k=list_k)
+    assert torch.equal(c0, c1) and torch.equal(a0, a1)                   # recording does not change the images
+    L = s1["L"]
+    T = ((W + 15) // 16) * ((H + 15) // 16)
+    flags = s1["ws"][L.tile_flag:L.tile_flag + 4 * V * T].view(torch.int32)
+    nl = s1["ws"][L.n_list:L.n_list + 4 * V * H * W].view(torch.int32)
+    assert int(nl.max()) > 3
+    if list_k == 3:
+        assert 0 < int(flags.sum()) <= V * T                             # overflowed tiles are flagged ...
+    else:
+        assert int(flags.sum()) == 0 and int(nl.max()) <= 32
+    g1 = raster.backward_raw(s1, dgc, dga)[0].cpu().numpy()
+    want = _oracle_grad_sum(g, vs, ps, bg, H, W, gc, ga, range(V))
+    for name, sl in GRAD_COLS:
+        assert rel_l2(g1[:, sl], want[:, sl]) <= TOL, (name, rel_l2(g1[:, sl], want[:, sl]))
+        assert rel_l2(g1[:, sl], g0[:, sl]) <= TOL, name

@@ -35,10 +35,11 @@ def main():
     dc = torch.randn(1, V, 3, H, W, device=dev)
     da = torch.randn(1, V, 7, H, W, device=dev)
     flush = torch.empty(256 << 20, device=dev, dtype=torch.uint8)
-    c, a, r, st = raster.forward_raw(g13, vm, pm, bg, H, W)
+    LK = int(os.environ.get("LISTK", str(raster.LIST_K)))
+    c, a, r, st = raster.forward_raw(g13, vm, pm, bg, H, W, list_k=LK)
     grad = raster.backward_raw(st, dc, da)
     for _ in range(3):
-        c, a, r, st = raster.forward_raw(g13, vm, pm, bg, H, W, max_instances=st["max_instances"])
+        c, a, r, st = raster.forward_raw(g13, vm, pm, bg, H, W, max_instances=st["max_instances"], list_k=LK)
         grad = raster.backward_raw(st, dc, da)
     torch.cuda.synchronize()
     lib.ga_profile_enable(1)
@@ -48,7 +49,7 @@ def main():
     for _ in range(steps):
         flush.zero_()
         e0.record()
-        c, a, r, st = raster.forward_raw(g13, vm, pm, bg, H, W, max_instances=st["max_instances"])
+        c, a, r, st = raster.forward_raw(g13, vm, pm, bg, H, W, max_instances=st["max_instances"], list_k=LK)
         grad = raster.backward_raw(st, dc, da)
         e1.record()
         e1.synchronize()
@@ -63,7 +64,8 @@ def main():
            "stage_us": dict(zip(["preprocess", "binning", "render_fwd", "render_bwd", "preprocess_bwd"], [round(1e3 * x, 1) for x in acc])),
            "sum_us": round(1e3 * acc.sum(), 1), "step_ms_incl_host": tot / steps,
            "check": {"color": float(c.double().sum()), "allmap": float(a.double().abs().sum()),
-                     "n_contrib": int(wsv["n_contrib"].long().sum()), "grad_abs": float(grad.double().abs().sum()),
+                     "n_contrib": int(wsv["n_contrib"].long().sum()), "list_k": LK,
+                     "flagged_tiles": (int(st["ws"][st["L"].tile_flag:st["L"].tile_flag + 4 * 6 * 1024].view(torch.int32).sum()) if LK else None), "grad_abs": float(grad.double().abs().sum()),
                      "grad_sum": float(grad.double().sum())}}
     print(json.dumps(out))
 
