@@ -499,6 +499,8 @@ gemm_bf16_tn_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
     cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem = tmem_slot;
+    pdl_wait();                     // inputs come from earlier kernels; everything above overlapped their tail
+    pdl_launch_dependents();
 
     if (warp == 0) {
         if (elect_one()) {

@@ -813,6 +813,9 @@ render_bwd_a_kernel(RasterDims d, RasterWs ws, BwdLists L, const float *__restri
         if (kk >= 0) e = __ldg(my_list + (size_t)kk * 256);
         if (kk >= 1) e1 = __ldg(my_list + (size_t)(kk - 1) * 256);
         if (kk >= 2) e2 = __ldg(my_list + (size_t)(kk - 2) * 256);
+#pragma unroll
+        for (int q = 3; q < 8; q++)
+            if (kk >= q) asm volatile("prefetch.global.L2 [%0];" ::"l"(my_list + (size_t)(kk - q) * 256));
     }
 
     if (threadIdx.x == 0) sm.maxc = 0;
@@ -893,6 +896,8 @@ render_bwd_a_kernel(RasterDims d, RasterWs ws, BwdLists L, const float *__restri
                     const uint4 cur = e;
                     e = e1; e1 = e2;
                     if (kk >= 3) e2 = __ldg(my_list + (size_t)(kk - 3) * 256);   // entries kk-1, kk-2, kk-3 are in flight
+                    // ... and the row 8 below is asked into L2 (the list rows stream from HBM exactly once)
+                    if (kk >= 8) asm volatile("prefetch.global.L2 [%0];" ::"l"(my_list + (size_t)(kk - 8) * 256));
                     kk--;
                     contribute(hi - 1 - (int)cur.x, (int)cur.x, __uint_as_float(cur.y), __uint_as_float(cur.z));
                 }
@@ -978,6 +983,9 @@ render_bwd_b_kernel(RasterDims d, RasterWs ws, BwdLists L, const float *__restri
     __shared__ int s_bin[64];
     __shared__ uint16_t s_perm[512];
     __shared__ int s_m;
+    // count / surfel id / slice start of the super-chunk's instances, loaded together while the sort runs: a pass then
+    // starts with ONE round trip (geometry record + first list records, independent) instead of four dependent ones
+    __shared__ uint32_t s_cnt[512], s_id[512], s_off[512];
     for (int c0 = 0; c0 < total; c0 += 512) {
         const int cn = min(512, total - c0);
         if (threadIdx.x < 64) s_bin[threadIdx.x] = 0;
@@ -987,6 +995,11 @@ render_bwd_b_kernel(RasterDims d, RasterWs ws, BwdLists L, const float *__restri
         for (int h = 0; h < 2; h++) {
             const int i = h * 256 + threadIdx.x;
             myn[h] = i < cn ? (int)L.inst_cnt[start + c0 + i] : 0;
+            if (i < cn) {
+                s_cnt[i] = (uint32_t)myn[h];
+                s_id[i] = ws.ids[start + c0 + i];
+                s_off[i] = L.inst_off[start + c0 + i];
+            }
             if (myn[h] > 0) atomicAdd(&s_bin[min(myn[h], 63)], 1);
         }
         __syncthreads();
@@ -1014,18 +1027,18 @@ render_bwd_b_kernel(RasterDims d, RasterWs ws, BwdLists L, const float *__restri
     for (int base = 0; base < m; base += IPB) {
         const int slot = base + threadIdx.x / TPI;
         const bool valid = slot < m;
-        const int inst = valid ? c0 + (int)s_perm[slot] : 0;
-        const int n = valid ? (int)L.inst_cnt[start + inst] : 0;
+        const int li = valid ? (int)s_perm[slot] : 0;
+        const int n = valid ? (int)s_cnt[li] : 0;
         float g[GA_GRAD_F];
 #pragma unroll
         for (int f = 0; f < GA_GRAD_F; f++) g[f] = 0.f;
         uint32_t id = 0;
         if (n > 0) {
-            id = ws.ids[start + inst];
+            id = s_id[li];
             const float4 *src = reinterpret_cast<const float4 *>(rec_base + (size_t)id * GA_REC_F);
             const float4 a = __ldg(src), b = __ldg(src + 1), c = __ldg(src + 2);
             const float opa = c.w;
-            const uint4 *lst = L.records + L.inst_off[start + inst];
+            const uint4 *lst = L.records + s_off[li];
             auto process = [&](const uint4 rc) {
                 const int pix = (int)rc.x;
                 const float dL_dalpha = __uint_as_float(rc.y), dL_dz = __uint_as_float(rc.z), w = __uint_as_float(rc.w);

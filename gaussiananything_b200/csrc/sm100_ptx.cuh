@@ -317,17 +317,32 @@ static inline cudaError_t ga_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim
     return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 
-// cluster launch (no PDL attribute: a dependent cluster kernel would have to co-reside with its predecessor)
+// cluster launch, with the PDL attribute as well (cluster dimension and programmatic stream serialisation are
+// independent launch attributes; round 1 launched cluster / pair kernels without PDL, which handicapped them in the
+// sweep: every launch then waits for the full drain of its predecessor)
 template <typename... KArgs, typename... Args>
 static inline cudaError_t ga_launch_cluster(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s,
                                             unsigned cluster_x, Args... args)
 {
+    static int use_pdl = -1;
+    if (use_pdl < 0) {
+        const char *e = getenv("GA_B200_PDL");
+        use_pdl = (e && e[0] == '0') ? 0 : 1;
+    }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = cluster_x; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = cluster_x > 1 ? 1 : 0;
+    cudaLaunchAttribute attr[2];
+    int n = 0;
+    if (cluster_x > 1) {
+        attr[n].id = cudaLaunchAttributeClusterDimension;
+        attr[n].val.clusterDim.x = cluster_x; attr[n].val.clusterDim.y = 1; attr[n].val.clusterDim.z = 1;
+        n++;
+    }
+    if (use_pdl) {
+        attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[n].val.programmaticStreamSerializationAllowed = 1;
+        n++;
+    }
+    cfg.attrs = attr; cfg.numAttrs = n;
     return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
-

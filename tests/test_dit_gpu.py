@@ -456,3 +456,30 @@ def test_inference_only_guard_and_parameter_updates():
         m.final_layer.linear.bias.mul_(2.0)
     y1 = m(x, t, ctx)
     assert rel(y1, 2.0 * y0) < 1e-5
+
+
+@pytest.mark.timeout(2400)
+def test_c4_size_forward_vs_oracle():
+    """BASELINE configs[3]: DiT-PixArt-PCD-CLAY-L (L24, D1024, H16) at N=4096, M=1369, CFG batch 2 -- stage 1 against
+    the oracle with bf16 operands emulated (minutes of CPU time on the GPU box's host cores; the size-independent
+    properties of stage 2 at this size are in test_dit_l_c4_size_properties)."""
+    from gaussiananything_b200 import dit
+    from oracle import dit_oracle as do
+    dev = torch.device("cuda:0")
+    torch.manual_seed(4)
+    torch.set_num_threads(os.cpu_count() or 1)
+    m = dit.DiT_models["DiT-PixArt-PCD-CLAY-L"](input_size=32, num_classes=0, learn_sigma=False, in_channels=3,
+                                                context_dim=1024, roll_out=True, pooling_ctx_dim=768)
+    m.randomize_zero_init_()
+    for p in m.parameters():
+        p.data.copy_(p.data.to(torch.bfloat16).float())
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    m.to(dev).eval()
+    B, N, M = 2, 4096, 1369
+    x, t = torch.randn(B, N, 3), torch.rand(B)
+    ctx = {"img_crossattn": torch.randn(B, M, 1024), "img_vector": torch.randn(B, 1024)}
+    y = m(x.to(dev), t.to(dev), {k: v.to(dev) for k, v in ctx.items()}).cpu()
+    with torch.no_grad():
+        want = do.forward(sd, x, t, ctx, 16, 24, emulate_bf16=True)
+    print("C4 size: output rel-L2 %.2e" % rel(y, want))
+    assert rel(y, want) < 8e-3, rel(y, want)

@@ -48,4 +48,16 @@ for (M, N, K) in shapes:
         b.record(); b.synchronize()
         us = a.elapsed_time(b) * 1e3 / 20
         row.append("%5d: %6.1fus %5.0fTF%s" % (cfg, us, 2.0 * M * N * K / us / 1e6, "" if err < 5e-3 else " ERR%.1e" % err))
+    # yardstick (not the product path): cuBLAS through torch.matmul on the same operands, bf16 output, no epilogue
+    if MODE == dit.EPI_BF16:
+        Wt = W.t().contiguous()
+        for _ in range(3):
+            torch.matmul(A, Wt)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(20):
+            torch.matmul(A, Wt)
+        b.record(); b.synchronize()
+        us = a.elapsed_time(b) * 1e3 / 20
+        row.append("cuBLAS: %6.1fus %5.0fTF" % (us, 2.0 * M * N * K / us / 1e6))
     print("M=%d N=%d K=%d | " % (M, N, K) + " | ".join(row), flush=True)
