@@ -13,6 +13,7 @@
 //    gradient over the warp with shuffles, over the CTA in shared memory, and
 //    issues one global atomic per (tile, surfel, component).
 #include "raster_common.cuh"
+#include "sm100_ptx.cuh"
 #include "device_once.cuh"
 #include <cstdlib>
 
@@ -739,13 +740,30 @@ __device__ __forceinline__ bool bwd_lists_overflow(const RasterDims &d, const Bw
     return L.tile_rec_start[d.NV * d.T] > L.capacity;
 }
 
+// LISTS: only the normal / colour records are needed in shared memory (alpha and depth come from the list entries);
+// the 16 KB that frees pay for a deeper ring of list rows
+template <bool LISTS>
 struct BwdASmem {
-    float4 rec[6][CHUNK];
+    float4 rec[LISTS ? 2 : 6][CHUNK];
     uint32_t off[CHUNK];            // start of the instance's slice, relative to the tile's base
     int cnt[CHUNK];
     uint32_t wsum[8];
-    int maxc;
+    int maxc, maxn;
 };
+
+#ifndef GA_BWD_A_TMA
+#define GA_BWD_A_TMA 1              /* list rows of single-chunk tiles through cp.async.bulk + mbarriers */
+#endif
+#define BWD_A_RING 9                /* 4 KB list rows in flight per CTA (static shared memory stays below 48 KB) */
+
+// 1-D bulk copy global -> shared with mbarrier completion (SASS: UBLKCP): one 4 KB list row per call
+__device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+                     sm100::smem_u32(smem_dst)),
+                 "l"(gsrc), "r"(bytes), "r"(sm100::smem_u32(bar))
+                 : "memory");
+}
 
 // LISTS = true: the pairs come from the per-pixel contribution lists the forward recorded (RasterWs.lists): every lane
 // walks ITS pixel's entries back to front -- {list position, alpha, depth} -- so there is no cull test, no pair
@@ -756,7 +774,8 @@ __global__ void __launch_bounds__(256, BWD_A_CTAS)
 render_bwd_a_kernel(RasterDims d, RasterWs ws, BwdLists L, const float *__restrict__ bg,
                     const float *__restrict__ dL_dcolor, const float *__restrict__ dL_dallmap)
 {
-    __shared__ BwdASmem sm;
+    __shared__ BwdASmem<LISTS> sm;
+    constexpr int REC_NR = LISTS ? 0 : 3, REC_GB = LISTS ? 1 : 5;
     if (ws.status[1] || bwd_lists_overflow(d, L)) return;
     const int view = blockIdx.z;
     const int tile = blockIdx.y * d.gx + blockIdx.x;
@@ -802,33 +821,69 @@ render_bwd_a_kernel(RasterDims d, RasterWs ws, BwdLists L, const float *__restri
     const float final_A = 1 - T_final;
     const float bg_dot_dpixel = bg[0] * dpx0 + bg[1] * dpx1 + bg[2] * dpx2;
     float last_alpha = 0, v_last = 0, v_acc = 0, last_dL_dT = 0;        // one scalar suffix recurrence (see the fused kernel)
-    // LISTS: this pixel's entries, walked from the last contribution to the first; `e` is the entry about to be used
-    // (three entries are kept in flight: one entry's math is ~60 instructions, a list row comes from L2 / HBM)
+    // LISTS: this pixel's entries, walked from the last contribution to the first.
+    //  * tiles whose surfel list fits one chunk (nearly all): ROW mode.  Row k of the tile's list array is one
+    //    contiguous 4 KB block {entry k of the 256 pixels}; thread 0 streams the rows the tile uses, last row first,
+    //    through a ring of BWD_A_RING shared-memory slots with cp.async.bulk + full/empty mbarriers (three rows ahead
+    //    of the consumers); at row k the lanes whose pixel has more than k contributions take their entry from the slot.
+    //  * longer tiles: every lane walks its own list with three entries in flight in registers (`e`, `e1`, `e2`).
     const uint4 *my_list = nullptr;
-    int kk = -1;
+    const char *tile_rows = nullptr;
+    int kk = -1, nl = 0;
     uint4 e = make_uint4(0u, 0u, 0u, 0u), e1 = e, e2 = e;
+    __shared__ __align__(128) uint4 s_rows[LISTS ? BWD_A_RING : 1][LISTS ? 256 : 1];
+    __shared__ uint64_t s_full[BWD_A_RING], s_empty[BWD_A_RING];
     if (LISTS) {
-        my_list = ws.lists + ((size_t)view * d.T + tile) * (size_t)d.list_k * 256 + pix_local;
-        kk = inside ? ws.n_list[(size_t)view * HW + pix] - 1 : -1;
-        if (kk >= 0) e = __ldg(my_list + (size_t)kk * 256);
-        if (kk >= 1) e1 = __ldg(my_list + (size_t)(kk - 1) * 256);
-        if (kk >= 2) e2 = __ldg(my_list + (size_t)(kk - 2) * 256);
-#pragma unroll
-        for (int q = 3; q < 8; q++)
-            if (kk >= q) asm volatile("prefetch.global.L2 [%0];" ::"l"(my_list + (size_t)(kk - q) * 256));
+        const uint4 *tl = ws.lists + ((size_t)view * d.T + tile) * (size_t)d.list_k * 256;
+        tile_rows = reinterpret_cast<const char *>(tl);
+        my_list = tl + pix_local;
+        nl = inside ? ws.n_list[(size_t)view * HW + pix] : 0;
     }
 
-    if (threadIdx.x == 0) sm.maxc = 0;
+    if (threadIdx.x == 0) {
+        sm.maxc = 0;
+        sm.maxn = 0;
+        if (LISTS) {
+#pragma unroll
+            for (int i = 0; i < BWD_A_RING; i++) { sm100::mbar_init(&s_full[i], 1); sm100::mbar_init(&s_empty[i], 8); }
+            sm100::fence_barrier_init();
+        }
+    }
     __syncthreads();
     {
-        int m = last_contributor;
+        int m = last_contributor, mn = nl;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
-        if (lane == 0) atomicMax(&sm.maxc, m);
+        for (int o = 16; o > 0; o >>= 1) {
+            m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+            mn = max(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        }
+        if (lane == 0) { atomicMax(&sm.maxc, m); atomicMax(&sm.maxn, mn); }
     }
     __syncthreads();
     const int total = sm.maxc;          // list positions [0,total) matter; the rest keep inst_cnt == 0 (memset)
     uint32_t run = 0;                   // records handed out to the chunks staged so far
+    const bool rows_mode = LISTS && GA_BWD_A_TMA && total <= CHUNK;          // block-uniform
+    const int maxn = sm.maxn;
+    auto issue_row = [&](const int j) {                                   // thread 0 only: j-th row in processing order
+        const int slot = j % BWD_A_RING, use = j / BWD_A_RING;
+        if (use > 0) sm100::mbar_wait(&s_empty[slot], (uint32_t)((use - 1) & 1));      // all 8 warps are done with its last row
+        sm100::mbar_expect_tx(&s_full[slot], 4096u);
+        bulk_g2s(&s_rows[slot][0], tile_rows + (size_t)(maxn - 1 - j) * 4096, 4096u, &s_full[slot]);
+    };
+    if (LISTS) {
+        if (rows_mode) {
+            if (threadIdx.x == 0)
+                for (int j = 0; j < min(maxn, BWD_A_RING - 2); j++) issue_row(j);
+        } else {
+            kk = nl - 1;
+            if (kk >= 0) e = __ldg(my_list + (size_t)kk * 256);
+            if (kk >= 1) e1 = __ldg(my_list + (size_t)(kk - 1) * 256);
+            if (kk >= 2) e2 = __ldg(my_list + (size_t)(kk - 2) * 256);
+#pragma unroll
+            for (int q = 3; q < 8; q++)
+                if (kk >= q) asm volatile("prefetch.global.L2 [%0];" ::"l"(my_list + (size_t)(kk - q) * 256));
+        }
+    }
 
     for (int hi = total; hi > 0; hi -= CHUNK) {
         const int lo = max(0, hi - CHUNK);
@@ -838,10 +893,18 @@ render_bwd_a_kernel(RasterDims d, RasterWs ws, BwdLists L, const float *__restri
         if ((int)threadIdx.x < cnt) {
             const uint32_t id = ws.ids[start + (hi - 1 - threadIdx.x)];
             const float4 *src = reinterpret_cast<const float4 *>(rec_base + (size_t)id * GA_REC_F);
-            float4 q[6];
+            float4 q4;
+            if (LISTS) {
+                sm.rec[REC_NR][threadIdx.x] = __ldg(src + 3);
+                sm.rec[REC_GB][threadIdx.x] = __ldg(src + 5);
+                q4 = __ldg(src + 4);
+            } else {
+                float4 q[6];
 #pragma unroll
-            for (int k = 0; k < 6; k++) { q[k] = __ldg(src + k); sm.rec[k][threadIdx.x] = q[k]; }
-            area = (uint32_t)clipped_box_area(q[4], ox, oy);
+                for (int k = 0; k < 6; k++) { q[k] = __ldg(src + k); sm.rec[k][threadIdx.x] = q[k]; }
+                q4 = q[4];
+            }
+            area = (uint32_t)clipped_box_area(q4, ox, oy);
         }
         uint32_t x = area;
 #pragma unroll
@@ -862,7 +925,7 @@ render_bwd_a_kernel(RasterDims d, RasterWs ws, BwdLists L, const float *__restri
 
         // one (pixel, surfel) contribution: the compositing recurrences backwards + the 16-byte record for kernel B
         auto contribute = [&](const int jj, const int contributor, const float alpha, const float c_d) {
-                    const float4 nr = sm.rec[3][jj], gb = sm.rec[5][jj];
+                    const float4 nr = sm.rec[REC_NR][jj], gb = sm.rec[REC_GB][jj];
                     const float inv1ma = fast_rcp(1.f - alpha);
                     T = T * inv1ma;
                     const float w = alpha * T;
@@ -888,7 +951,19 @@ render_bwd_a_kernel(RasterDims d, RasterWs ws, BwdLists L, const float *__restri
                     L.records[(size_t)tile_base + sm.off[jj] + (uint32_t)slot] =
                         make_uint4((uint32_t)pix_local, __float_as_uint(dL_dalpha), __float_as_uint(dL_dz), __float_as_uint(w));
         };
-        if (LISTS) {
+        if (LISTS && rows_mode) {
+            for (int j = 0; j < maxn; j++) {
+                const int k = maxn - 1 - j, slot = j % BWD_A_RING;
+                if (threadIdx.x == 0 && j + BWD_A_RING - 2 < maxn) issue_row(j + BWD_A_RING - 2);
+                sm100::mbar_wait(&s_full[slot], (uint32_t)((j / BWD_A_RING) & 1));
+                if (nl > k) {
+                    const uint4 cur = s_rows[slot][pix_local];
+                    contribute(hi - 1 - (int)cur.x, (int)cur.x, __uint_as_float(cur.y), __uint_as_float(cur.z));
+                }
+                __syncwarp();
+                if (lane == 0) sm100::mbar_arrive(&s_empty[slot]);          // this warp has read row k out of the slot
+            }
+        } else if (LISTS) {
             while (true) {
                 const bool active = kk >= 0 && (int)e.x >= lo;      // entries are in descending list position
                 if (!__any_sync(0xffffffffu, active)) break;
@@ -902,7 +977,7 @@ render_bwd_a_kernel(RasterDims d, RasterWs ws, BwdLists L, const float *__restri
                     contribute(hi - 1 - (int)cur.x, (int)cur.x, __uint_as_float(cur.y), __uint_as_float(cur.z));
                 }
             }
-        } else {
+        } else if constexpr (!LISTS) {
         for (int sb = 0; sb < cnt; sb += 32) {
             bool hit = false;
             if (sb + lane < cnt) {
