@@ -108,3 +108,20 @@ def test_dit_module_has_reference_state_dict_layout():
         m(g["x"], g["t"], g["ctx"])
     m2 = dit.DiT_models["DiT-PixArt-PCD-CLAY-stage2-L"]
     assert callable(m2) and set(dit.DiT_models) >= {"DiT-PixArt-PCD-CLAY-L", "DiT-PixArt-PCD-CLAY-B"}
+
+
+@pytest.mark.parametrize("name,cin", [("DiT-PixArt-PCD-CLAY-B", 3), ("DiT-PixArt-PCD-CLAY-L", 3),
+                                      ("DiT-PixArt-PCD-CLAY-stage2-L", 10)])
+def test_registry_entries_load_reference_checkpoints_strictly(name, cin):
+    """The mirror modules have EXACTLY the reference's state_dict keys and shapes (fixture written by
+    tests/golden/make_dit_keys.py from the reference's own registry entries): load_state_dict(strict=True) works."""
+    import json
+    import torch
+    from gaussiananything_b200 import dit
+    want = json.load(open(os.path.join(GOLD, "dit_state_dict_keys.json")))[name]
+    with torch.device("meta"):                      # shapes only: DiT-L is 1.6 GB of fp32 parameters
+        m = dit.DiT_models[name](input_size=32, num_classes=0, learn_sigma=False, in_channels=cin, context_dim=1024,
+                                 roll_out=True, pooling_ctx_dim=768)
+    got = {k: list(v.shape) for k, v in m.state_dict().items()}
+    assert sorted(got) == sorted(want), (sorted(set(want) - set(got))[:5], sorted(set(got) - set(want))[:5])
+    assert got == want

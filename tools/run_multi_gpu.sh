@@ -1,4 +1,4 @@
 cd /root/repo
-N=$1
+N=${1:-8}      # usage (under gpurun --gpus N): bash tools/run_multi_gpu.sh N
 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus $N --steps 50 > gpurun_out/bench_n$N.json 2> gpurun_out/bench_n$N.err
 tail -3 gpurun_out/bench_n$N.err

@@ -39,9 +39,11 @@ for d in rows:
         n, c["views_per_s"], c["views_per_s"] / n, (c["views_per_s"] / n) / (b5["views_per_s"] / base["n_gpus"]), st["vae_decode"],
         co["us_max_over_ranks"], co["bytes_total"] / 1e6, ("%.0f" % co["algbw_GBs"]) if co.get("algbw_GBs") else "-", st["render_shard"],
         ("%.3f" % cas["samples_per_s"]) if cas else "-", ("%.3f" % (cas["samples_per_s"] / n)) if cas else "-"))
-out += ["", "The all-gather moves 3.83 MB per rank; it is issued through torch.distributed (NCCL's own stream, ordered against the",
-        "compute stream by events), so the figure includes that hand-off.  Rendering after the gather is rank-local: each rank",
-        "renders 8 of the N x 8 (sample, view) pairs in one batched launch set.", ""]
+out += ["", "The all-gather moves 3.83 MB per rank.  Its time is the interval between two CUDA events on the compute stream around",
+        "torch.distributed's call (NCCL's own stream, ordered against the compute stream by events), so it contains the stream",
+        "hand-off AND the wait for the slowest rank's decode to reach the collective (arrival skew), not only the NVLink transfer",
+        "(11.5 MB received per rank at N = 4 is ~15 us at the measured 770 GB/s).  Rendering after the gather is rank-local: each",
+        "rank renders 8 of the N x 8 (sample, view) pairs in one batched launch set.", ""]
 path = os.path.join(ROOT, "profiles", "r02_scale_c5.md")
 open(path, "w").write("\n".join(out))
 print(path)
