@@ -333,10 +333,11 @@ def run_gpu(args):
         ev_done.record()
         state["done"] = ev_done
 
-    # >= 20 warm-up steps, then >= 500 steps AND >= 2 s (round 1 timed 20 steps = 29 ms after 3 warm-up steps: one
+    # 50 warm-up steps, then >= 500 steps AND >= 2 s (round 1 timed 20 steps = 29 ms after 3 warm-up steps: one
     # allocator / engine stall made BENCH and SCALE N=1 disagree 24x).  Per-step host times are kept: the mean gives
     # the throughput, the median / p99 / max show whether a stall was inside the window.
-    for _ in range(20):
+    E2E_WARMUP = 50
+    for _ in range(E2E_WARMUP):
         step_e2e()
     state["done"].synchronize()
     torch.cuda.synchronize(dev)
@@ -364,7 +365,8 @@ def run_gpu(args):
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
     e2e_value = float(t.item())
     step_s = np.array(step_s)
-    e2e_stats = {"steps": e2e_steps, "seconds": e_local, "warmup_steps": 20,
+    e2e_stats = {"steps": e2e_steps, "seconds": e_local, "warmup_steps": E2E_WARMUP,
+                 "slow_step_indices": [int(i) for i in np.nonzero(step_s > 5 * np.median(step_s))[0][:12]],
                  "ms_per_step_mean": 1e3 * e_local / e2e_steps, "ms_per_step_median": 1e3 * float(np.median(step_s)),
                  "ms_per_step_p99": 1e3 * float(np.percentile(step_s, 99)), "ms_per_step_max": 1e3 * float(step_s.max()),
                  "steps_over_5x_median": int((step_s > 5 * np.median(step_s)).sum()),
