@@ -454,6 +454,11 @@ def run_gpu(args):
                "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": hbm, "unit": "GB/s",
                             "frac": achieved / hbm, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                             "algorithmic_bytes_per_launch": dom_bytes,
+                            # what the hardware actually moved (ncu dram__bytes of the stage's kernels, profiles/traffic.json)
+                            # over the live stage time: round 2's backward trades bytes (per-pixel lists, record slices)
+                            # for instructions, so it moves ~4.6x the algorithmic bytes on purpose
+                            "traffic_GBs": (traffic / (stages[dom] * 1e-3) / 1e9) if traffic else None,
+                            "traffic_frac": (traffic / (stages[dom] * 1e-3) / 1e9 / hbm) if traffic else None,
                             "whole_step_algorithmic_GBs": step_bytes / (dev_ms_max / args.steps * 1e-3) / 1e9,
                             "whole_step_frac": step_bytes / (dev_ms_max / args.steps * 1e-3) / 1e9 / hbm, "fp32": fp32},
                "cpu_baseline": ({"value": cpu_v, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
