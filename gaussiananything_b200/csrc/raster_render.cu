@@ -321,8 +321,11 @@ cudaError_t ga_launch_render_fwd(const RasterDims &d, const RasterWs &w, const f
 #ifndef BWD_B_UNROLL
 #define BWD_B_UNROLL 2              /* records per loop iteration and lane in kernel B */
 #endif
+#ifndef BWD_B_THREADS
+#define BWD_B_THREADS 128           /* threads per CTA (= per tile) in kernel B: 128 -> 6 CTAs per SM; 256: +22 us, 64: +56 us on C2 */
+#endif
 #ifndef BWD_B_CTAS
-#define BWD_B_CTAS 3
+#define BWD_B_CTAS (768 / BWD_B_THREADS)
 #endif
 #ifndef BWD_B_TPI
 #define BWD_B_TPI 2                 /* lanes per instance in kernel B (2: 364 us, 4: 375 us, 8: 400+ us on C2) */
@@ -1016,7 +1019,7 @@ render_bwd_a_kernel(RasterDims d, RasterWs ws, BwdLists L, const float *__restri
 }
 
 template <int TPI>
-__global__ void __launch_bounds__(256, BWD_B_CTAS)
+__global__ void __launch_bounds__(BWD_B_THREADS, BWD_B_CTAS)
 render_bwd_b_kernel(RasterDims d, RasterWs ws, BwdLists L, const float *__restrict__ dL_dcolor,
                     const float *__restrict__ dL_dallmap, float *__restrict__ grad_acc, const int tile_filter)
 {
@@ -1033,7 +1036,8 @@ render_bwd_b_kernel(RasterDims d, RasterWs ws, BwdLists L, const float *__restri
     const int total = (int)(end - start);
     if (total == 0) return;
     {
-        const int lxi = threadIdx.x & 15, lyi = threadIdx.x >> 4;
+      for (int px = threadIdx.x; px < 256; px += BWD_B_THREADS) {
+        const int lxi = px & 15, lyi = px >> 4;
         const int pxi = ox + lxi, pyi = oy + lyi;
         float4 ua = make_float4(0.f, 0.f, 0.f, 0.f), ub = ua;
         if (pxi < d.W && pyi < d.H) {
@@ -1043,15 +1047,17 @@ render_bwd_b_kernel(RasterDims d, RasterWs ws, BwdLists L, const float *__restri
             ua = make_float4(gc[pix], gc[pix + HW], gc[pix + 2 * HW], ga[pix + 2 * HW]);
             ub = make_float4(ga[pix + 3 * HW], ga[pix + 4 * HW], 0.f, 0.f);
         }
-        s_up[0][threadIdx.x] = ua;              // index = ly * 16 + lx = the records' pixel field
-        s_up[1][threadIdx.x] = ub;
+        s_up[0][px] = ua;              // index = ly * 16 + lx = the records' pixel field
+        s_up[1][px] = ub;
+      }
     }
     __syncthreads();
     const float *rec_base = ws.rec + (size_t)view * d.P * GA_REC_F;
     float *acc_base = grad_acc + (size_t)view * d.P * GA_GRAD_F;
     const int lane = threadIdx.x & 31;
     const int sub = threadIdx.x % TPI;
-    constexpr int IPB = 256 / TPI;              // instances per pass
+    constexpr int IPB = BWD_B_THREADS / TPI;    // instances per pass
+    constexpr int NH = 512 / BWD_B_THREADS;     // instances each thread files in the counting sort
     // Instances carry 0 .. ~30 records; a warp's pass lasts as long as its longest instance.  So the tile's instances
     // are handled in super-chunks of 512: a counting sort by record count (descending, empty ones dropped) decides
     // which instance each lane group takes, and every warp gets instances of similar length.
@@ -1065,10 +1071,10 @@ render_bwd_b_kernel(RasterDims d, RasterWs ws, BwdLists L, const float *__restri
         const int cn = min(512, total - c0);
         if (threadIdx.x < 64) s_bin[threadIdx.x] = 0;
         __syncthreads();
-        int myn[2];
+        int myn[NH];
 #pragma unroll
-        for (int h = 0; h < 2; h++) {
-            const int i = h * 256 + threadIdx.x;
+        for (int h = 0; h < NH; h++) {
+            const int i = h * BWD_B_THREADS + threadIdx.x;
             myn[h] = i < cn ? (int)L.inst_cnt[start + c0 + i] : 0;
             if (i < cn) {
                 s_cnt[i] = (uint32_t)myn[h];
@@ -1095,8 +1101,8 @@ render_bwd_b_kernel(RasterDims d, RasterWs ws, BwdLists L, const float *__restri
         }
         __syncthreads();
 #pragma unroll
-        for (int h = 0; h < 2; h++)
-            if (myn[h] > 0) s_perm[atomicAdd(&s_bin[min(myn[h], 63)], 1)] = (uint16_t)(h * 256 + threadIdx.x);
+        for (int h = 0; h < NH; h++)
+            if (myn[h] > 0) s_perm[atomicAdd(&s_bin[min(myn[h], 63)], 1)] = (uint16_t)(h * BWD_B_THREADS + threadIdx.x);
         __syncthreads();
         const int m = s_m;
     for (int base = 0; base < m; base += IPB) {
@@ -1234,19 +1240,19 @@ cudaError_t ga_launch_render_bwd(const RasterDims &d, const RasterWs &w, const f
                 cudaEventRecord(g->fork, s);
                 cudaStreamWaitEvent(g->st, g->fork, 0);
                 render_bwd_a_kernel<false><<<grid, 256, 0, g->st>>>(d, w, lists, bg, dL_dcolor, dL_dallmap);
-                render_bwd_b_kernel<BWD_B_TPI><<<grid, 256, 0, g->st>>>(d, w, lists, dL_dcolor, dL_dallmap, grad_acc, 2);
+                render_bwd_b_kernel<BWD_B_TPI><<<grid, BWD_B_THREADS, 0, g->st>>>(d, w, lists, dL_dcolor, dL_dallmap, grad_acc, 2);
                 cudaEventRecord(g->join, g->st);
                 render_bwd_a_kernel<true><<<grid, 256, 0, s>>>(d, w, lists, bg, dL_dcolor, dL_dallmap);
-                render_bwd_b_kernel<BWD_B_TPI><<<grid, 256, 0, s>>>(d, w, lists, dL_dcolor, dL_dallmap, grad_acc, 1);
+                render_bwd_b_kernel<BWD_B_TPI><<<grid, BWD_B_THREADS, 0, s>>>(d, w, lists, dL_dcolor, dL_dallmap, grad_acc, 1);
                 cudaStreamWaitEvent(s, g->join, 0);
             } else {
                 render_bwd_a_kernel<true><<<grid, 256, 0, s>>>(d, w, lists, bg, dL_dcolor, dL_dallmap);
                 render_bwd_a_kernel<false><<<grid, 256, 0, s>>>(d, w, lists, bg, dL_dcolor, dL_dallmap);
-                render_bwd_b_kernel<BWD_B_TPI><<<grid, 256, 0, s>>>(d, w, lists, dL_dcolor, dL_dallmap, grad_acc, 0);
+                render_bwd_b_kernel<BWD_B_TPI><<<grid, BWD_B_THREADS, 0, s>>>(d, w, lists, dL_dcolor, dL_dallmap, grad_acc, 0);
             }
         } else {
             render_bwd_a_kernel<false><<<grid, 256, 0, s>>>(d, w, lists, bg, dL_dcolor, dL_dallmap);
-            render_bwd_b_kernel<BWD_B_TPI><<<grid, 256, 0, s>>>(d, w, lists, dL_dcolor, dL_dallmap, grad_acc, 0);
+            render_bwd_b_kernel<BWD_B_TPI><<<grid, BWD_B_THREADS, 0, s>>>(d, w, lists, dL_dcolor, dL_dallmap, grad_acc, 0);
         }
     }
     // fused kernel: the whole job when the split path is off, a no-op or the fallback (record buffer too small) otherwise
