@@ -213,11 +213,17 @@ __device__ __forceinline__ void warp_sort_tile(unsigned long long *gk, uint32_t 
 }
 
 // one warp per tile (tiles with more than SORT_WARP_MAX instances are left to sort_tiles_kernel)
-__global__ void __launch_bounds__(256)
+#ifndef SORT_WARP_THREADS
+#define SORT_WARP_THREADS 256
+#endif
+#ifndef SORT_WARP_CTAS
+#define SORT_WARP_CTAS (512 / SORT_WARP_THREADS)
+#endif
+__global__ void __launch_bounds__(SORT_WARP_THREADS, SORT_WARP_CTAS)
 sort_tiles_warp_kernel(RasterDims d, RasterWs ws)
 {
     if (ws.status[1]) return;
-    const size_t t = (size_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const size_t t = (size_t)blockIdx.x * (SORT_WARP_THREADS / 32) + (threadIdx.x >> 5);
     if (t >= (size_t)d.NV * d.T) return;
     const int lane = threadIdx.x & 31;
     const uint32_t start = ws.tile_start[t], end = ws.tile_start[t + 1];
@@ -287,10 +293,10 @@ cudaError_t ga_launch_binning(const RasterDims &d, const RasterWs &w, cudaStream
         cudaStreamWaitEvent(g->st, g->fork, 0);
         sort_tiles_kernel<<<big_grid, 256, 0, g->st>>>(d, w);
         cudaEventRecord(g->join, g->st);
-        sort_tiles_warp_kernel<<<(d.NV * d.T + 7) / 8, 256, 0, s>>>(d, w);
+        sort_tiles_warp_kernel<<<(d.NV * d.T + SORT_WARP_THREADS / 32 - 1) / (SORT_WARP_THREADS / 32), SORT_WARP_THREADS, 0, s>>>(d, w);
         cudaStreamWaitEvent(s, g->join, 0);
     } else {
-        sort_tiles_warp_kernel<<<(d.NV * d.T + 7) / 8, 256, 0, s>>>(d, w);
+        sort_tiles_warp_kernel<<<(d.NV * d.T + SORT_WARP_THREADS / 32 - 1) / (SORT_WARP_THREADS / 32), SORT_WARP_THREADS, 0, s>>>(d, w);
         sort_tiles_kernel<<<big_grid, 256, 0, s>>>(d, w);
     }
     return cudaGetLastError();

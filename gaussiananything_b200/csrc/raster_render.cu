@@ -18,6 +18,9 @@
 #include <cstdlib>
 
 #define CHUNK 256
+#ifndef GA_LIST_STCS
+#define GA_LIST_STCS 0
+#endif
 #ifndef GA_FWD_GROUP_DEFAULT
 #define GA_FWD_GROUP_DEFAULT 8
 #endif
@@ -226,9 +229,15 @@ render_fwd_kernel(RasterDims d, RasterWs ws, const float *__restrict__ bg,
                         T = test_T;
                         last_contributor = contributor;
                         if (LISTS) {
-                            if (nl < d.list_k)
-                                my_list[(size_t)nl * 256] = make_uint4((uint32_t)(contributor - 1), __float_as_uint(alpha),
-                                                                       __float_as_uint(depth), 0u);
+                            if (nl < d.list_k) {
+                                const uint4 ent = make_uint4((uint32_t)(contributor - 1), __float_as_uint(alpha),
+                                                             __float_as_uint(depth), 0u);
+#if GA_LIST_STCS
+                                __stcs(my_list + (size_t)nl * 256, ent);       // written once, read once by the backward
+#else
+                                my_list[(size_t)nl * 256] = ent;
+#endif
+                            }
                             nl++;
                         }
                     }
