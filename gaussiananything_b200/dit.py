@@ -77,12 +77,16 @@ _GEMM_CFG_ENV = None
 
 
 def _gemm_config(M, N, mode=None):
-    """Tile width (+ 1000 * cluster size, ga_b200.h).  Measured on B200 (tools/sweep_gemm.py,
-    profiles/r01_gemm_sweep.txt): the main loop is bound by the SM's shared-memory port (operand reads + TMA fills), so
-    wider tiles are more efficient per byte, but only pay when the tile count still fills the 148 SMs evenly.
-    128 x 128 is the default; the residual-update GEMMs with N = 768 (192 tiles of 128 x 128 = 1.3 waves) run as
-    128 tiles of 128 x 192 in a single wave: 14.6 -> 12.7 us (K = 768), 25.9 -> 21.8 us (K = 3072).
-    GA_B200_GEMM_CFG="big,small" overrides."""
+    """Tile width (+ 1000 * cluster size, ga_b200.h) from a two-term cost model fitted to the round-2 sweep
+    (tools/sweep_gemm.py, profiles/r02_gemm_sweep.txt, cuBLAS column as yardstick):
+
+        cost(BN) = ceil(tiles(BN) / 148) * (BN + 64)
+
+    -- waves of the persistent grid times the per-tile work (the main loop scales with BN, the +64 is the fixed
+    TMA-fill / epilogue-drain share that makes wide tiles more efficient per byte).  It reproduces the measured winner on
+    all nine DiT shapes: 192 for 4096x768 (K = 768: 8.1 vs 9.5 us; K = 3072: 16.6 vs 21.8), 4096x3072 and 1536x4096,
+    256 for 4096x2304 and 1536x3072, 128 for the under-filled 1536x1024 GEMMs of the deployed size.
+    The HEADS epilogue (whole 64-wide heads per half tile: 128 or 256 only) stays at 128.  GA_B200_GEMM_CFG="big,small" overrides."""
     global _GEMM_CFG_ENV
     if _GEMM_CFG_ENV is None:
         import os
@@ -90,11 +94,18 @@ def _gemm_config(M, N, mode=None):
     if _GEMM_CFG_ENV:
         big, small = (int(v) for v in _GEMM_CFG_ENV.split(","))
         return big if (M >= 1024 and N >= 512) else small
-    tiles128 = -(-M // 128) * -(-N // 128)
-    tiles192 = -(-M // 128) * -(-N // 192)
-    if mode == EPI_RESID_GATE_F32 and N % 192 == 0 and tiles128 > 148 and tiles192 <= 148:
-        return 192
-    return 128
+    rows = -(-M // 128)
+    best, best_cost = 128, None
+    if mode == EPI_HEADS:
+        return 128                      # 256-wide HEADS tiles measured slower at M = 1536 (deployed qkv: +1.7 % per NFE)
+    for bn in (128, 192, 256):
+        if bn > 128 and N < bn:
+            continue
+        tiles = rows * -(-N // bn)
+        cost = -(-tiles // 148) * (bn + 64)
+        if best_cost is None or cost < best_cost:
+            best, best_cost = bn, cost
+    return best
 
 
 def _round_up(x, m):
