@@ -584,9 +584,19 @@ def run_vae_decoder_leg(dev, reps=5):
     e1.record()
     e1.synchronize()
     ms = e0.elapsed_time(e1) / reps / B
+    # latency of one sample alone (the C5 path decodes one sample per rank)
+    for _ in range(2):
+        dec.decode(lat[:1], xyz[:1])
+    torch.cuda.synchronize(dev)
+    e0.record()
+    for _ in range(reps):
+        dec.decode(lat[:1], xyz[:1])
+    e1.record()
+    e1.synchronize()
+    ms1 = e0.elapsed_time(e1) / reps
     return {"config": "N1: VAE decoder, 768 tokens x 768, DiT2-B + cascade 8*4*3 -> 73728 surfels/sample, batch 2, bf16",
             "ms_per_sample": ms, "samples_per_s": 1e3 / ms, "tflops": decode_flops(768, 12) / (ms * 1e-3) / 1e12,
-            "surfels_per_sample": 73728}
+            "ms_batch1": ms1, "cuda_graph": bool(dec.use_graph), "surfels_per_sample": 73728}
 
 
 def run_dit_deployed_leg(dev, nfe=20, N=768, samples=1):

@@ -148,9 +148,12 @@ thin_linear_kernel(const float *__restrict__ x, const float *__restrict__ ln_w, 
 
 // Attention over micro-sequences: qkv bf16 [S*L, 3*H*64] in "(K H D)" column order (q | k | v), per-head RMSNorm of
 // q and k (weights qn_w, kn_w [64]), softmax(q k^T / 8) v, out bf16 [S*L, H*64].  One warp per (sequence, head); the
-// L x 64 tiles live in shared memory as fp32 (rows padded to 65 floats: conflict-free column walks).
+// L x 64 tiles live in shared memory as fp32 (rows padded to 65 floats: conflict-free column walks).  The footprint is
+// sized by the actual L (5, 9, 4 rows in the deployed cascade, not the maximum 16): 3.2-7.4 KB per warp, so 28-64 warps
+// stay resident per SM -- the kernel is a 1.5 KB-in / 0.5 KB-out stream per item and lives on loads in flight (round 2:
+// with the fixed 13.5 KB footprint only 16 warps were resident and the kernel ran at 1/7 of the HBM rate).
 constexpr int kMicroL = 16, kMicroPitch = 65, kMicroWarps = 4;
-constexpr int kMicroSmemPerWarp = (3 * kMicroL * kMicroPitch + kMicroL * (kMicroL + 1)) * (int)sizeof(float);
+__host__ __device__ constexpr int micro_floats_per_warp(int L) { return 3 * L * kMicroPitch + L * (L + 1); }
 
 __global__ void __launch_bounds__(32 * kMicroWarps)
 micro_attention_kernel(const __nv_bfloat16 *__restrict__ qkv, const float *__restrict__ qn_w,
@@ -161,20 +164,36 @@ micro_attention_kernel(const __nv_bfloat16 *__restrict__ qkv, const float *__res
     const long long item = (long long)blockIdx.x * kMicroWarps + warp;
     if (item >= (long long)S * H) return;
     const int s = (int)(item / H), h = (int)(item % H);
-    float *sq = micro_smem + (size_t)warp * (kMicroSmemPerWarp / sizeof(float));
-    float *sk = sq + kMicroL * kMicroPitch, *sv = sk + kMicroL * kMicroPitch, *sp = sv + kMicroL * kMicroPitch;
+    const int LP = L + 1;
+    float *sq = micro_smem + (size_t)warp * micro_floats_per_warp(L);
+    float *sk = sq + L * kMicroPitch, *sv = sk + L * kMicroPitch, *sp = sv + L * kMicroPitch;
     const int C = H * 64;
     const float wq0 = qn_w[2 * lane], wq1 = qn_w[2 * lane + 1], wk0 = kn_w[2 * lane], wk1 = kn_w[2 * lane + 1];
-    for (int i = 0; i < L; i++) {
-        const __nv_bfloat16 *row = qkv + ((size_t)s * L + i) * (3 * C) + h * 64 + 2 * lane;
-        const float2 q = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(row));
-        const float2 k = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(row + C));
-        const float2 v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(row + 2 * C));
-        const float rq = rsqrtf(wsum(q.x * q.x + q.y * q.y) * (1.0f / 64.0f) + eps);
-        const float rk = rsqrtf(wsum(k.x * k.x + k.y * k.y) * (1.0f / 64.0f) + eps);
-        sq[i * kMicroPitch + 2 * lane] = q.x * rq * wq0; sq[i * kMicroPitch + 2 * lane + 1] = q.y * rq * wq1;
-        sk[i * kMicroPitch + 2 * lane] = k.x * rk * wk0; sk[i * kMicroPitch + 2 * lane + 1] = k.y * rk * wk1;
-        sv[i * kMicroPitch + 2 * lane] = v.x; sv[i * kMicroPitch + 2 * lane + 1] = v.y;
+    const __nv_bfloat16 *base = qkv + (size_t)s * L * (3 * C) + h * 64 + 2 * lane;
+    for (int i0 = 0; i0 < L; i0 += 4) {
+        // up to 12 independent 128-byte row segments per warp are requested before the first reduction needs one
+        __nv_bfloat162 rq[4], rk[4], rv[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            if (i0 + u < L) {
+                const __nv_bfloat16 *row = base + (size_t)(i0 + u) * (3 * C);
+                rq[u] = *reinterpret_cast<const __nv_bfloat162 *>(row);
+                rk[u] = *reinterpret_cast<const __nv_bfloat162 *>(row + C);
+                rv[u] = *reinterpret_cast<const __nv_bfloat162 *>(row + 2 * C);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            if (i0 + u < L) {
+                const int i = i0 + u;
+                const float2 q = __bfloat1622float2(rq[u]), k = __bfloat1622float2(rk[u]), v = __bfloat1622float2(rv[u]);
+                const float nq = rsqrtf(wsum(q.x * q.x + q.y * q.y) * (1.0f / 64.0f) + eps);
+                const float nk = rsqrtf(wsum(k.x * k.x + k.y * k.y) * (1.0f / 64.0f) + eps);
+                sq[i * kMicroPitch + 2 * lane] = q.x * nq * wq0; sq[i * kMicroPitch + 2 * lane + 1] = q.y * nq * wq1;
+                sk[i * kMicroPitch + 2 * lane] = k.x * nk * wk0; sk[i * kMicroPitch + 2 * lane + 1] = k.y * nk * wk1;
+                sv[i * kMicroPitch + 2 * lane] = v.x; sv[i * kMicroPitch + 2 * lane + 1] = v.y;
+            }
+        }
     }
     __syncwarp();
     for (int e = lane; e < L * L; e += 32) {                  // scores, scaled by 1/sqrt(64)
@@ -182,26 +201,26 @@ micro_attention_kernel(const __nv_bfloat16 *__restrict__ qkv, const float *__res
         float a = 0.f;
 #pragma unroll 16
         for (int d = 0; d < 64; d++) a += sq[i * kMicroPitch + d] * sk[j * kMicroPitch + d];
-        sp[i * (kMicroL + 1) + j] = a * 0.125f;
+        sp[i * LP + j] = a * 0.125f;
     }
     __syncwarp();
     if (lane < L) {                                           // one lane per query row
         float m = -INFINITY;
-        for (int j = 0; j < L; j++) m = fmaxf(m, sp[lane * (kMicroL + 1) + j]);
+        for (int j = 0; j < L; j++) m = fmaxf(m, sp[lane * LP + j]);
         float l = 0.f;
         for (int j = 0; j < L; j++) {
-            const float p = __expf(sp[lane * (kMicroL + 1) + j] - m);
-            sp[lane * (kMicroL + 1) + j] = p;
+            const float p = __expf(sp[lane * LP + j] - m);
+            sp[lane * LP + j] = p;
             l += p;
         }
         const float inv = 1.0f / l;
-        for (int j = 0; j < L; j++) sp[lane * (kMicroL + 1) + j] *= inv;
+        for (int j = 0; j < L; j++) sp[lane * LP + j] *= inv;
     }
     __syncwarp();
     for (int i = 0; i < L; i++) {
         float o0 = 0.f, o1 = 0.f;
         for (int j = 0; j < L; j++) {
-            const float p = sp[i * (kMicroL + 1) + j];
+            const float p = sp[i * LP + j];
             o0 += p * sv[j * kMicroPitch + 2 * lane];
             o1 += p * sv[j * kMicroPitch + 2 * lane + 1];
         }
@@ -311,12 +330,12 @@ extern "C" int ga_micro_attention_bf16(const void *qkv, const float *qn_w, const
     static GaPerDevice attr_set;
     if (ga_first_use_on_device(attr_set)) {
         cudaError_t e = cudaFuncSetAttribute(micro_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             kMicroWarps * kMicroSmemPerWarp);
+                                             kMicroWarps * micro_floats_per_warp(kMicroL) * (int)sizeof(float));
         if (e != cudaSuccess) return (int)e;
     }
     const long long items = (long long)S * H;
     micro_attention_kernel<<<(unsigned)((items + kMicroWarps - 1) / kMicroWarps), 32 * kMicroWarps,
-                             kMicroWarps * kMicroSmemPerWarp, (cudaStream_t)stream>>>(
+                             kMicroWarps * micro_floats_per_warp(L) * sizeof(float), (cudaStream_t)stream>>>(
         reinterpret_cast<const __nv_bfloat16 *>(qkv), qn_w, kn_w, reinterpret_cast<__nv_bfloat16 *>(out), S, L, H, eps);
     return last_err();
 }

@@ -12,6 +12,7 @@ Mirrors what the reference's deployed decoder class does between DiT sampling an
 up-samplers' micro-sequences, row kernels).  bf16 tensor-core operands, fp32 residual streams.  No CPU fallback.
 """
 import ctypes as C
+import os
 
 import torch
 
@@ -95,6 +96,8 @@ class SurfelDecoder:
                                     h_w=f32(p + "gaussian_residual_pred.fn.weight"),
                                     h_b=f32(p + "gaussian_residual_pred.fn.bias")))
         self.w = w
+        self.use_graph = os.environ.get("GA_B200_VAE_GRAPH", "1") != "0"
+        self._graphs = {}                                  # batch size -> (graph, static latent, static xyz, static outputs)
 
     @staticmethod
     def _attn_mlp(pa, pm, f32, b16):
@@ -119,12 +122,50 @@ class SurfelDecoder:
         return e
 
     def decode(self, latent_normalized, query_pcd_xyz):
-        """latent_normalized [B, N, Cz], query_pcd_xyz [B, N, 3] (CUDA).  Returns the reference's ret_dict entries."""
-        L, w, dev = self.L, self.w, self.device
+        """latent_normalized [B, N, Cz], query_pcd_xyz [B, N, 3] (CUDA).  Returns the reference's ret_dict entries.
+
+        The ~300 launches of one decode are captured once per batch size into a CUDA graph and replayed from static input
+        buffers (at batch 1 the eager launch sequence is host-bound); the returned tensors are copies, so they stay
+        valid across later calls.  `self.use_graph = False` (or GA_B200_VAE_GRAPH=0) keeps the eager launch sequence."""
+        dev = self.device
         if not latent_normalized.is_cuda:
             raise RuntimeError("gaussiananything_b200 VAE decoder needs CUDA tensors (no CPU fallback)")
         B, N, zc = latent_normalized.shape
         assert N == self.N and zc == self.zc and query_pcd_xyz.shape == (B, N, 3)
+        with torch.cuda.device(dev):               # launches go to the decoder's device, not the process's current one
+            if not self.use_graph or torch.cuda.is_current_stream_capturing():
+                return self._aliases(self._decode_launches(latent_normalized, query_pcd_xyz))
+            slot = self._graphs.get(B)
+            if slot is None:
+                # buffers and graph are created outside inference_mode so that later calls may come from either mode
+                with torch.inference_mode(False), torch.no_grad():
+                    s_lat = torch.empty(B, N, zc, device=dev, dtype=torch.float32)
+                    s_xyz = torch.empty(B, N, 3, device=dev, dtype=torch.float32)
+                    s_lat.copy_(latent_normalized)
+                    s_xyz.copy_(query_pcd_xyz)
+                    self._decode_launches(s_lat, s_xyz)            # warm-up: first-use kernel attributes are set here
+                    torch.cuda.synchronize(dev)
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        outs = self._decode_launches(s_lat, s_xyz)
+                slot = self._graphs[B] = (g, s_lat, s_xyz, outs)
+            g, s_lat, s_xyz, outs = slot
+            s_lat.copy_(latent_normalized)
+            s_xyz.copy_(query_pcd_xyz)
+            g.replay()
+            return self._aliases({k: v.clone() for k, v in outs.items()})
+
+    @staticmethod
+    def _aliases(out):
+        out["gaussians"] = out["gaussians_upsampled"]                  # forward_gaussians: "only adopt SR"
+        out["pos"] = out["gaussians"][..., :3]
+        out["gaussians_base_opa"] = out["gaussians_base"][..., 3:4]
+        return out
+
+    def _decode_launches(self, latent_normalized, query_pcd_xyz):
+        """The launch sequence of one decode on the current stream (eager, or under graph capture)."""
+        L, w, dev = self.L, self.w, self.device
+        B, N, zc = latent_normalized.shape
         D, H, R, dep = self.D, self.H, B * N, self.depth
         st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
         z = lambda *s, dt=torch.float32: torch.empty(*s, device=dev, dtype=dt)
@@ -199,9 +240,6 @@ class SurfelDecoder:
                                          self.scale_factor, _p(g), _p(pre), Rc, st), "cascade pack")
             out["gaussians_upsampled" + ("" if si == 0 else "_%d" % (si + 1))] = g.view(B, Rc // B, 13)
             parents, prev_f, parent_g, parent_pre, S = seq, f, g, pre, Rc
-        out["gaussians"] = out["gaussians_upsampled"]                  # forward_gaussians: "only adopt SR"
-        out["pos"] = out["gaussians"][..., :3]
-        out["gaussians_base_opa"] = out["gaussians_base"][..., 3:4]
         return out
 
 

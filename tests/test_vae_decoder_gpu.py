@@ -119,3 +119,37 @@ def test_surfel_ae_dropin_behaviours_and_multi_lod_render():
     assert "gaussians_upsampled_3" in full
     with pytest.raises(NotImplementedError):
         ae(img=torch.zeros(1), behaviour="enc")
+
+
+def test_graph_replay_matches_eager_launches_bit_for_bit():
+    """decode() replays a CUDA graph captured per batch size; the eager launch sequence (use_graph=False) must give the
+    same bits, new inputs must reach the static buffers, returned tensors must survive later calls, and a call from
+    torch.inference_mode (the reference's eval path) must work before and after the capture."""
+    from oracle import vae_decoder_oracle as vo
+    from gaussiananything_b200.vae_decoder import SurfelDecoder
+    g = vo.load_golden(GOLD)
+    dev = torch.device("cuda:0")
+    dec = SurfelDecoder(g["sd"], g["heads"], g["depth"], g["scene_max"], g["skip_weight"], device=dev)
+    lat, xyz = g["latent"].to(dev), g["xyz"].to(dev)
+    torch.manual_seed(3)
+    lat2 = lat + 0.3 * torch.randn_like(lat)
+    dec.use_graph = False
+    eager1, eager2, eager_one = dec.decode(lat, xyz), dec.decode(lat2, xyz), dec.decode(lat[:1], xyz[:1])
+    assert not dec._graphs
+    dec.use_graph = True
+    with torch.inference_mode():
+        first = dec.decode(lat, xyz)                    # captures
+    assert lat.shape[0] in dec._graphs
+    second = dec.decode(lat2, xyz)                      # replays with new inputs
+    with torch.inference_mode():
+        third = dec.decode(lat, xyz)
+    torch.cuda.synchronize()
+    for k in eager1:
+        assert torch.equal(first[k], eager1[k]), k
+        assert torch.equal(second[k], eager2[k]), k
+        assert torch.equal(third[k], eager1[k]), k
+    assert not torch.equal(first["gaussians"], second["gaussians"])
+    # a different batch size gets its own graph
+    one = dec.decode(lat[:1], xyz[:1])
+    assert torch.equal(one["gaussians_upsampled_3"], eager_one["gaussians_upsampled_3"])
+    assert set(dec._graphs) == {lat.shape[0], 1}
