@@ -81,67 +81,98 @@ layernorm_modulate_kernel(const float *__restrict__ x, const float *__restrict__
     }
 }
 
-// y[r, c] = b[c] + sum_d f(x[r])[d] W[c, d], f = [LayerNorm affine] then [SiLU]; one warp per row; C <= 16
+// y[r, c] = b[c] + sum_d f(x[r])[d] W[c, d], f = [LayerNorm affine] then [SiLU]; C <= 16.  One warp per THIN_ROWS rows:
+// the C x D weight (40 KB at 13 x 768) comes through L1 once per warp-iteration, so with one row per warp the kernel was
+// bound by L1 bandwidth (13 weight loads per x load), not by the x stream; two rows share every weight load.  Per-row
+// arithmetic (order of the partial sums, the butterfly reductions) does not depend on THIN_ROWS.
+#ifndef GA_THIN_ROWS
+#define GA_THIN_ROWS 2
+#endif
+constexpr int THIN_ROWS = GA_THIN_ROWS;
+
 __global__ void __launch_bounds__(256)
 thin_linear_kernel(const float *__restrict__ x, const float *__restrict__ ln_w, const float *__restrict__ ln_b,
                    int apply_silu, const float *__restrict__ W, const float *__restrict__ bias,
                    float *__restrict__ y, int R, int D, int C, float eps)
 {
-    const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int r0 = (blockIdx.x * 8 + (threadIdx.x >> 5)) * THIN_ROWS;
     const int lane = threadIdx.x & 31;
-    if (r >= R) return;
-    const float4 *x4 = reinterpret_cast<const float4 *>(x + (size_t)r * D);
+    if (r0 >= R) return;
     const int n4 = D >> 2;
-    float4 c[8];
-    float s = 0.f;
+    float4 c[THIN_ROWS][8];
+    float mean[THIN_ROWS], rs[THIN_ROWS];
 #pragma unroll
-    for (int u = 0; u < 8; u++) {
-        const int i = lane + 32 * u;
-        c[u] = i < n4 ? x4[i] : make_float4(0.f, 0.f, 0.f, 0.f);
-        s += (c[u].x + c[u].y) + (c[u].z + c[u].w);
-    }
-    float mean = 0.f, rs = 1.f;
-    if (ln_w) {
-        mean = wsum(s) / (float)D;
-        float v = 0.f;
+    for (int q = 0; q < THIN_ROWS; q++) {
+        const int r = min(r0 + q, R - 1);                   // a missing last row re-reads the previous one (not stored)
+        const float4 *x4 = reinterpret_cast<const float4 *>(x + (size_t)r * D);
 #pragma unroll
         for (int u = 0; u < 8; u++) {
-            if (lane + 32 * u < n4) {
-                const float d0 = c[u].x - mean, d1 = c[u].y - mean, d2 = c[u].z - mean, d3 = c[u].w - mean;
-                v += d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
-            }
+            const int i = lane + 32 * u;
+            c[q][u] = i < n4 ? x4[i] : make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        rs = rsqrtf(wsum(v) / (float)D + eps);
     }
-    float acc[16];
 #pragma unroll
-    for (int k = 0; k < 16; k++) acc[k] = 0.f;
+    for (int q = 0; q < THIN_ROWS; q++) {
+        mean[q] = 0.f; rs[q] = 1.f;
+        if (ln_w) {
+            float s = 0.f;
+#pragma unroll
+            for (int u = 0; u < 8; u++) s += (c[q][u].x + c[q][u].y) + (c[q][u].z + c[q][u].w);
+            mean[q] = wsum(s) / (float)D;
+            float v = 0.f;
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                if (lane + 32 * u < n4) {
+                    const float d0 = c[q][u].x - mean[q], d1 = c[q][u].y - mean[q], d2 = c[q][u].z - mean[q], d3 = c[q][u].w - mean[q];
+                    v += d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
+                }
+            }
+            rs[q] = rsqrtf(wsum(v) / (float)D + eps);
+        }
+    }
+    float acc[THIN_ROWS][16];
+#pragma unroll
+    for (int q = 0; q < THIN_ROWS; q++)
+#pragma unroll
+        for (int k = 0; k < 16; k++) acc[q][k] = 0.f;
 #pragma unroll
     for (int u = 0; u < 8; u++) {
         const int i = lane + 32 * u;
         if (i < n4) {
-            float4 h = c[u];
+            float4 h[THIN_ROWS];
+            float4 ww = make_float4(1.f, 1.f, 1.f, 1.f), bb = make_float4(0.f, 0.f, 0.f, 0.f);
             if (ln_w) {
-                const float4 ww = __ldg(reinterpret_cast<const float4 *>(ln_w) + i);
-                const float4 bb = ln_b ? __ldg(reinterpret_cast<const float4 *>(ln_b) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-                h.x = (h.x - mean) * rs * ww.x + bb.x; h.y = (h.y - mean) * rs * ww.y + bb.y;
-                h.z = (h.z - mean) * rs * ww.z + bb.z; h.w = (h.w - mean) * rs * ww.w + bb.w;
+                ww = __ldg(reinterpret_cast<const float4 *>(ln_w) + i);
+                if (ln_b) bb = __ldg(reinterpret_cast<const float4 *>(ln_b) + i);
             }
-            if (apply_silu) { h.x = silu_f(h.x); h.y = silu_f(h.y); h.z = silu_f(h.z); h.w = silu_f(h.w); }
+#pragma unroll
+            for (int q = 0; q < THIN_ROWS; q++) {
+                h[q] = c[q][u];
+                if (ln_w) {
+                    h[q].x = (h[q].x - mean[q]) * rs[q] * ww.x + bb.x; h[q].y = (h[q].y - mean[q]) * rs[q] * ww.y + bb.y;
+                    h[q].z = (h[q].z - mean[q]) * rs[q] * ww.z + bb.z; h[q].w = (h[q].w - mean[q]) * rs[q] * ww.w + bb.w;
+                }
+                if (apply_silu) { h[q].x = silu_f(h[q].x); h[q].y = silu_f(h[q].y); h[q].z = silu_f(h[q].z); h[q].w = silu_f(h[q].w); }
+            }
 #pragma unroll
             for (int k = 0; k < 16; k++) {
                 if (k < C) {
                     const float4 wk = __ldg(reinterpret_cast<const float4 *>(W + (size_t)k * D) + i);
-                    acc[k] += h.x * wk.x + h.y * wk.y + h.z * wk.z + h.w * wk.w;
+#pragma unroll
+                    for (int q = 0; q < THIN_ROWS; q++)
+                        acc[q][k] += h[q].x * wk.x + h[q].y * wk.y + h[q].z * wk.z + h[q].w * wk.w;
                 }
             }
         }
     }
 #pragma unroll
-    for (int k = 0; k < 16; k++) {
-        if (k < C) {
-            const float t = wsum(acc[k]);
-            if (lane == 0) y[(size_t)r * C + k] = t + (bias ? bias[k] : 0.f);
+    for (int q = 0; q < THIN_ROWS; q++) {
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            if (k < C) {
+                const float t = wsum(acc[q][k]);
+                if (lane == 0 && r0 + q < R) y[(size_t)(r0 + q) * C + k] = t + (bias ? bias[k] : 0.f);
+            }
         }
     }
 }
@@ -155,7 +186,10 @@ thin_linear_kernel(const float *__restrict__ x, const float *__restrict__ ln_w, 
 constexpr int kMicroL = 16, kMicroPitch = 65, kMicroWarps = 4;
 __host__ __device__ constexpr int micro_floats_per_warp(int L) { return 3 * L * kMicroPitch + L * (L + 1); }
 
-__global__ void __launch_bounds__(32 * kMicroWarps)
+#ifndef GA_MICRO_MIN_CTAS
+#define GA_MICRO_MIN_CTAS 1
+#endif
+__global__ void __launch_bounds__(32 * kMicroWarps, GA_MICRO_MIN_CTAS)
 micro_attention_kernel(const __nv_bfloat16 *__restrict__ qkv, const float *__restrict__ qn_w,
                        const float *__restrict__ kn_w, __nv_bfloat16 *__restrict__ out, int S, int L, int H, float eps)
 {
@@ -319,7 +353,7 @@ extern "C" int ga_thin_linear(const float *x, const float *ln_w, const float *ln
                               const float *bias, float *y, int R, int D, int C, float eps, void *stream)
 {
     if (!x || !W || !y || R <= 0 || !row_ok(D) || C <= 0 || C > 16 || (ln_b && !ln_w)) return GA_ERR_BADARG;
-    thin_linear_kernel<<<(R + 7) / 8, 256, 0, (cudaStream_t)stream>>>(x, ln_w, ln_b, apply_silu, W, bias, y, R, D, C, eps);
+    thin_linear_kernel<<<(R + 8 * THIN_ROWS - 1) / (8 * THIN_ROWS), 256, 0, (cudaStream_t)stream>>>(x, ln_w, ln_b, apply_silu, W, bias, y, R, D, C, eps);
     return last_err();
 }
 
