@@ -146,7 +146,9 @@ class SurfelDecoder:
                     self._decode_launches(s_lat, s_xyz)            # warm-up: first-use kernel attributes are set here
                     torch.cuda.synchronize(dev)
                     g = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(g):
+                    # thread_local: another thread of the process (NCCL's watchdog under torch.distributed) may issue
+                    # CUDA calls while this one captures
+                    with torch.cuda.graph(g, capture_error_mode="thread_local"):
                         outs = self._decode_launches(s_lat, s_xyz)
                 slot = self._graphs[B] = (g, s_lat, s_xyz, outs)
             g, s_lat, s_xyz, outs = slot
