@@ -21,6 +21,27 @@ __device__ __forceinline__ float wsum(float v)
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
+// Warp sums of N values at once (N a power of two <= 32): at every butterfly step a lane keeps one half of its values
+// and hands the other half to its partner, so N totals cost N - 1 + log2(32 / N) shuffles instead of 5 N.  Lane l ends
+// up with the total of value index (l >> log2(32 / N)) & (N - 1); the additions are the ones the plain butterfly makes,
+// in the same order, so the totals are bit-identical to wsum().
+template <int N>
+__device__ __forceinline__ float packed_wsum(float (&v)[N], int lane)
+{
+    int n = N, o = 16;
+#pragma unroll
+    for (; n > 1; n >>= 1, o >>= 1) {
+        const bool upper = (lane & o) != 0;
+#pragma unroll
+        for (int m = 0; m < n / 2; m++) {
+            const float keep = upper ? v[m + n / 2] : v[m], send = upper ? v[m] : v[m + n / 2];
+            v[m] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+        }
+    }
+#pragma unroll
+    for (; o > 0; o >>= 1) v[0] += __shfl_xor_sync(0xffffffffu, v[0], o);
+    return v[0];
+}
 __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
 
 // one warp per row, row cached in registers (D % 4 == 0, D <= 1024)
@@ -186,10 +207,10 @@ thin_linear_kernel(const float *__restrict__ x, const float *__restrict__ ln_w, 
 constexpr int kMicroL = 16, kMicroPitch = 65, kMicroWarps = 4;
 __host__ __device__ constexpr int micro_floats_per_warp(int L) { return 3 * L * kMicroPitch + L * (L + 1); }
 
-#ifndef GA_MICRO_MIN_CTAS
-#define GA_MICRO_MIN_CTAS 1
+#ifndef GA_MICRO_SMALL
+#define GA_MICRO_SMALL 1          // 0: every length goes through the generic kernel below
 #endif
-__global__ void __launch_bounds__(32 * kMicroWarps, GA_MICRO_MIN_CTAS)
+__global__ void __launch_bounds__(32 * kMicroWarps)
 micro_attention_kernel(const __nv_bfloat16 *__restrict__ qkv, const float *__restrict__ qn_w,
                        const float *__restrict__ kn_w, __nv_bfloat16 *__restrict__ out, int S, int L, int H, float eps)
 {
@@ -257,6 +278,122 @@ micro_attention_kernel(const __nv_bfloat16 *__restrict__ qkv, const float *__res
             const float p = sp[i * LP + j];
             o0 += p * sv[j * kMicroPitch + 2 * lane];
             o1 += p * sv[j * kMicroPitch + 2 * lane + 1];
+        }
+        *reinterpret_cast<__nv_bfloat162 *>(out + ((size_t)s * L + i) * C + h * 64 + 2 * lane) = __floats2bfloat162_rn(o0, o1);
+    }
+}
+
+// The deployed cascade's sequence lengths (1 + f = 9, 5, 4) get a compile-time-L version of the same algorithm: q and k
+// rows at a 68-float pitch (16-byte aligned: the 64-long dot products run on LDS.128, and consecutive rows start 4 banks
+// apart, so the <= 8 distinct rows one quarter-warp touches never collide), v stays in the loading lane's registers (each
+// lane owns two head dims of every row), every loop is unrolled and e / L, e % L are constants.  ~380 warp instructions
+// per (sequence, head) item at L = 4 against ~1 090 for the generic kernel, which ncu showed issue-bound (77 % issue-active,
+// 19 % of the DRAM rate) once its occupancy was fixed.
+template <int L>
+__global__ void __launch_bounds__(32 * kMicroWarps)
+micro_attention_small_kernel(const __nv_bfloat16 *__restrict__ qkv, const float *__restrict__ qn_w,
+                             const float *__restrict__ kn_w, __nv_bfloat16 *__restrict__ out, int S, int H, float eps)
+{
+    constexpr bool SPLIT = L == 4;                                // 2 L^2 = 32: two lanes share one dot product
+    constexpr int PITCH = SPLIT ? 72 : 68, LP = L + 1;            // split: rows 8 banks apart, the two halves 4 apart
+    constexpr int PER_WARP = (2 * L * PITCH + L * LP + 3) & ~3;
+    __shared__ __align__(16) float smem[kMicroWarps * PER_WARP];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const unsigned item = blockIdx.x * kMicroWarps + warp;        // the launcher keeps S * H below 2^31
+    if (item >= (unsigned)S * (unsigned)H) return;                // warps are independent: no block-wide barrier below
+    const unsigned s = item / (unsigned)H, h = item - s * (unsigned)H;
+    float *sq = smem + warp * PER_WARP, *sk = sq + L * PITCH, *sp = sk + L * PITCH;
+    const int C = H * 64;
+    const float2 wq = *reinterpret_cast<const float2 *>(qn_w + 2 * lane), wk = *reinterpret_cast<const float2 *>(kn_w + 2 * lane);
+    const __nv_bfloat16 *base = qkv + (size_t)s * L * (3 * C) + h * 64 + 2 * lane;
+    __nv_bfloat162 rq[L], rk[L], rv[L];
+#pragma unroll
+    for (int i = 0; i < L; i++) {                                 // 3 L independent 128-byte row segments per warp
+        const __nv_bfloat16 *row = base + (size_t)i * (3 * C);
+        rq[i] = *reinterpret_cast<const __nv_bfloat162 *>(row);
+        rk[i] = *reinterpret_cast<const __nv_bfloat162 *>(row + C);
+        rv[i] = *reinterpret_cast<const __nv_bfloat162 *>(row + 2 * C);
+    }
+    float2 q[L], k[L], v[L];
+    constexpr int NP = L <= 4 ? 8 : (L <= 8 ? 16 : 32);           // 2 L sums of squares, padded to a power of two
+    constexpr int SH = NP == 8 ? 2 : (NP == 16 ? 1 : 0);
+    float ssq[NP];
+#pragma unroll
+    for (int i = 0; i < NP; i++) ssq[i] = 0.f;
+#pragma unroll
+    for (int i = 0; i < L; i++) {
+        q[i] = __bfloat1622float2(rq[i]); k[i] = __bfloat1622float2(rk[i]); v[i] = __bfloat1622float2(rv[i]);
+        ssq[2 * i] = q[i].x * q[i].x + q[i].y * q[i].y;
+        ssq[2 * i + 1] = k[i].x * k[i].x + k[i].y * k[i].y;
+    }
+    const float rn = rsqrtf(packed_wsum<NP>(ssq, lane) * (1.0f / 64.0f) + eps);     // this lane's one RMS factor
+#pragma unroll
+    for (int i = 0; i < L; i++) {
+        const float nq = __shfl_sync(0xffffffffu, rn, (2 * i) << SH), nk = __shfl_sync(0xffffffffu, rn, (2 * i + 1) << SH);
+        *reinterpret_cast<float2 *>(sq + i * PITCH + 2 * lane) = make_float2(q[i].x * nq * wq.x, q[i].y * nq * wq.y);
+        *reinterpret_cast<float2 *>(sk + i * PITCH + 2 * lane) = make_float2(k[i].x * nk * wk.x, k[i].y * nk * wk.y);
+    }
+    __syncwarp();
+    if constexpr (SPLIT) {                                        // scores: lane pair per (i, j), alternate 16-byte chunks
+        const int e = lane >> 1, half = lane & 1;
+        const int i = e / L, j = e % L;
+        const float4 *q4 = reinterpret_cast<const float4 *>(sq + (e < L * L ? i : 0) * PITCH) + half;
+        const float4 *k4 = reinterpret_cast<const float4 *>(sk + (e < L * L ? j : 0) * PITCH) + half;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+        for (int d = 0; d < 8; d++) {
+            const float4 a = q4[2 * d], b = k4[2 * d];
+            a0 += a.x * b.x; a1 += a.y * b.y; a2 += a.z * b.z; a3 += a.w * b.w;
+        }
+        float a = (a0 + a1) + (a2 + a3);
+        a += __shfl_xor_sync(0xffffffffu, a, 1);
+        // every lane now holds one score; the four (i, .) scores sit in the lanes l, l^2, l^4, l^6: softmax by shuffles
+        const float sc = a * 0.125f;
+        float m = fmaxf(sc, __shfl_xor_sync(0xffffffffu, sc, 2));
+        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 4));
+        const float pe = __expf(sc - m);
+        float l = pe + __shfl_xor_sync(0xffffffffu, pe, 2);
+        l += __shfl_xor_sync(0xffffffffu, l, 4);
+        if (half == 0) sp[i * LP + j] = pe * (1.0f / l);
+    } else
+#pragma unroll
+    for (int e0 = 0; e0 < L * L; e0 += 32) {                      // scores, scaled by 1/sqrt(64): one lane per (i, j)
+        const int e = e0 + lane;
+        if (e < L * L) {
+            const int i = e / L, j = e % L;
+            const float4 *q4 = reinterpret_cast<const float4 *>(sq + i * PITCH);
+            const float4 *k4 = reinterpret_cast<const float4 *>(sk + j * PITCH);
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+            for (int d = 0; d < 16; d++) {
+                const float4 a = q4[d], b = k4[d];
+                a0 += a.x * b.x; a1 += a.y * b.y; a2 += a.z * b.z; a3 += a.w * b.w;
+            }
+            sp[i * LP + j] = ((a0 + a1) + (a2 + a3)) * 0.125f;
+        }
+    }
+    __syncwarp();
+    if (!SPLIT && lane < L) {                                     // one lane per query row
+        float pr[L];
+        float m = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < L; j++) { pr[j] = sp[lane * LP + j]; m = fmaxf(m, pr[j]); }
+        float l = 0.f;
+#pragma unroll
+        for (int j = 0; j < L; j++) { pr[j] = __expf(pr[j] - m); l += pr[j]; }
+        const float inv = 1.0f / l;
+#pragma unroll
+        for (int j = 0; j < L; j++) sp[lane * LP + j] = pr[j] * inv;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < L; i++) {
+        float o0 = 0.f, o1 = 0.f;
+#pragma unroll
+        for (int j = 0; j < L; j++) {
+            const float pij = sp[i * LP + j];                     // same address in every lane: a broadcast
+            o0 += pij * v[j].x;
+            o1 += pij * v[j].y;
         }
         *reinterpret_cast<__nv_bfloat162 *>(out + ((size_t)s * L + i) * C + h * 64 + 2 * lane) = __floats2bfloat162_rn(o0, o1);
     }
@@ -368,6 +505,17 @@ extern "C" int ga_micro_attention_bf16(const void *qkv, const float *qn_w, const
         if (e != cudaSuccess) return (int)e;
     }
     const long long items = (long long)S * H;
+    const unsigned grid = (unsigned)((items + kMicroWarps - 1) / kMicroWarps);
+    const __nv_bfloat16 *qp = reinterpret_cast<const __nv_bfloat16 *>(qkv);
+    __nv_bfloat16 *op = reinterpret_cast<__nv_bfloat16 *>(out);
+#if GA_MICRO_SMALL
+    if ((L == 4 || L == 5 || L == 9) && items < (1ll << 31)) {
+        if (L == 4) micro_attention_small_kernel<4><<<grid, 32 * kMicroWarps, 0, (cudaStream_t)stream>>>(qp, qn_w, kn_w, op, S, H, eps);
+        else if (L == 5) micro_attention_small_kernel<5><<<grid, 32 * kMicroWarps, 0, (cudaStream_t)stream>>>(qp, qn_w, kn_w, op, S, H, eps);
+        else micro_attention_small_kernel<9><<<grid, 32 * kMicroWarps, 0, (cudaStream_t)stream>>>(qp, qn_w, kn_w, op, S, H, eps);
+        return last_err();
+    }
+#endif
     micro_attention_kernel<<<(unsigned)((items + kMicroWarps - 1) / kMicroWarps), 32 * kMicroWarps,
                              kMicroWarps * micro_floats_per_warp(L) * sizeof(float), (cudaStream_t)stream>>>(
         reinterpret_cast<const __nv_bfloat16 *>(qkv), qn_w, kn_w, reinterpret_cast<__nv_bfloat16 *>(out), S, L, H, eps);
