@@ -43,6 +43,7 @@ def _bind():
 
 class SurfelDecoder:
     CASCADE = (("ada_CA_f4_1", 8), ("ada_CA_f4_2", 4), ("ada_CA_f4_3", 3))
+    MAX_GRAPHS = 4                 # captured batch sizes kept at a time (oldest dropped first)
 
     def __init__(self, state_dict, num_heads, depth, scene_max=0.45, skip_weight=0.1, device="cuda:0"):
         self.L = _bind()
@@ -137,6 +138,8 @@ class SurfelDecoder:
                 return self._aliases(self._decode_launches(latent_normalized, query_pcd_xyz))
             slot = self._graphs.get(B)
             if slot is None:
+                while len(self._graphs) >= self.MAX_GRAPHS:        # each graph owns its activations (GBs at the deployed size)
+                    self._graphs.pop(next(iter(self._graphs)))
                 # buffers and graph are created outside inference_mode so that later calls may come from either mode
                 with torch.inference_mode(False), torch.no_grad():
                     s_lat = torch.empty(B, N, zc, device=dev, dtype=torch.float32)
