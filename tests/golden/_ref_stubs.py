@@ -84,6 +84,13 @@ sys.meta_path.append(_Finder())
 # ---- torchdiffeq stub: fixed-grid solvers exactly on the given time grid (torchdiffeq FixedGridODESolver semantics)
 def odeint(func, y0, t, *, method='dopri5', atol=None, rtol=None, **kw):
     assert method in ('euler','midpoint','rk4','heun2','heun'), method
+    if isinstance(y0, tuple):
+        # torchdiffeq flattens a tuple state into one tensor, solves, and returns a tuple of per-component stacks
+        shapes = [c.shape for c in y0]; sizes = [c[0].numel() if c.dim() > 1 else 1 for c in y0]; B = y0[0].shape[0]
+        flat = lambda cs: torch.cat([c.reshape(B, -1) for c in cs], 1)
+        unflat = lambda y: tuple(p.reshape(sh) for p, sh in zip(torch.split(y, sizes, 1), shapes))
+        out = odeint(lambda tt, y: flat(func(tt, unflat(y))), flat(y0), t, method=method)
+        return tuple(torch.stack([unflat(o)[i] for o in out], 0) for i in range(len(y0)))
     ys=[y0]; y=y0
     for i in range(len(t)-1):
         t0,t1=t[i],t[i+1]; dt=t1-t0
