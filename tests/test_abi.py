@@ -84,3 +84,33 @@ def test_install_shims_registers_reference_module_names():
                 sys.modules.pop(k, None)
             else:
                 sys.modules[k] = v
+
+
+def test_missing_library_fails_loudly_everywhere():
+    """No CPU fallback anywhere on the product path: with the shared library absent the rasteriser, the DiT binding and
+    the VAE decoder all raise (checked in a child process so this process keeps its loaded library)."""
+    import subprocess
+    import sys
+    code = (
+        "import torch\n"
+        "from gaussiananything_b200 import _lib, raster, dit, vae_decoder\n"
+        "n = 0\n"
+        "for f in (_lib.lib, dit._bind, vae_decoder._bind,\n"
+        "          lambda: raster.layout(1, 10, 1, 32, 32, 100)):\n"
+        "    try:\n"
+        "        f()\n"
+        "    except RuntimeError as e:\n"
+        "        assert 'no CPU fallback' in str(e) or 'missing' in str(e), e\n"
+        "        n += 1\n"
+        "print('raised', n)\n")
+    env = dict(os.environ, GA_B200_LIB="/nonexistent/libga_b200.so")
+    out = subprocess.run([sys.executable, "-c", code], cwd=ROOT, env=env, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "raised 4" in out.stdout, out.stdout + out.stderr[-1000:]
+
+
+def test_decoder_refuses_cpu_devices():
+    """(The DiT modules' CPU refusal is in tests/test_oracle_dit.py::test_dit_module_has_reference_state_dict_layout.)"""
+    from gaussiananything_b200.vae_decoder import SurfelDecoder
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        SurfelDecoder({}, 12, 12, device="cpu")
