@@ -88,3 +88,104 @@ def test_camera_helper_matches_reference_fixture_layout():
     # row-vector convention: [p,1] @ view has z = distance along the optical axis
     z = (np.array([0, 0, 0, 1.0]) @ view)[2]
     assert abs(z - np.linalg.norm(pose[[3, 7, 11]])) < 1e-3
+
+
+# ---- known-answer tests: the oracle against closed-form geometry written down independently of it -------------------
+def _ka_camera(H, W, F=1.2):
+    from tools import synth
+    pose = np.concatenate([np.eye(4).reshape(-1), np.array([F, 0, .5, 0, F, .5, 0, 0, 1.])]).astype(np.float32)
+    view, proj, _, tanfov = synth.camera_from_pose25(pose)           # camera at the origin looking down +z
+    py, px = np.mgrid[0:H, 0:W].astype(np.float64)
+    return view, proj, tanfov, px, py, ((2 * px + 1) / W - 1) * tanfov, ((2 * py + 1) / H - 1) * tanfov
+
+
+def _ka_rot(q):
+    w, x, y, z = np.asarray(q, float) / np.linalg.norm(q)
+    return np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y)],
+                     [2 * (x * y + w * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w * x)],
+                     [2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)]])
+
+
+def _ka_surfel(P0, s, q, o, cam, H, W):
+    """Ray / plane intersection of every pixel's ray with the surfel's plane, local (u, v) in units of the scales, the
+    2DGS low-pass (rho2d = 2 |pixel - box centre|^2), alpha = min(0.99, o exp(-min(rho3d, rho2d) / 2)) dropped below
+    1/255, depth = hit depth (centre depth where the low-pass wins), normal turned towards the camera."""
+    _, _, tanfov, px, py, dx, dy = cam
+    R = _ka_rot(q)
+    tu, tv, n = R[:, 0], R[:, 1], R[:, 2]
+    d = np.stack([dx, dy, np.ones_like(dx)], -1)
+    t = (P0 @ n) / (d @ n)
+    h = d * t[..., None]
+    u, v = ((h - P0) @ tu) / s[0], ((h - P0) @ tv) / s[1]
+    rho3 = u * u + v * v
+    # upstream centres its screen-space low-pass on the centre of the bounding box of the projected 3-sigma ellipse
+    # (compute_aabb's `center`, not the projected splat centre): here from 40 000 projected boundary points
+    phi = np.linspace(0.0, 2 * np.pi, 40001)[:-1]
+    rim = P0[None] + 3.0 * (np.cos(phi)[:, None] * s[0] * tu[None] + np.sin(phi)[:, None] * s[1] * tv[None])
+    rx = ((rim[:, 0] / rim[:, 2] / tanfov + 1) * W - 1) * 0.5
+    ry = ((rim[:, 1] / rim[:, 2] / tanfov + 1) * H - 1) * 0.5
+    cx, cy = 0.5 * (rx.min() + rx.max()), 0.5 * (ry.min() + ry.max())
+    rho2 = 2.0 * ((px - cx) ** 2 + (py - cy) ** 2)
+    depth = np.where(rho3 <= rho2, h[..., 2], P0[2])
+    a = np.minimum(0.99, o * np.exp(-0.5 * np.minimum(rho3, rho2)))
+    a = np.where((a < 1.0 / 255.0) | (depth < 0.2), 0.0, a)
+    return a, depth, (n if (P0 @ n) < 0 else -n)
+
+
+def _ka_run(surfels, cam, H, W, bg):
+    P0 = np.array([s[0] for s in surfels], np.float32)
+    sc = np.array([s[1] for s in surfels], np.float32)
+    q = np.array([s[2] for s in surfels], np.float32)
+    o = np.array([s[3] for s in surfels], np.float32)
+    col = np.array([s[4] for s in surfels], np.float32)
+    return so.rasterize(P0, o, sc, q, col, cam[0], cam[1], bg, H, W)
+
+
+def test_known_answer_single_tilted_surfel():
+    """Alpha, colour, expected depth, median depth and the camera-facing normal of one surfel tilted 35 degrees: the
+    homography-based intersection of the oracle against plain ray / plane geometry."""
+    H = W = 64
+    cam = _ka_camera(H, W)
+    bg = np.array([0.1, 0.2, 0.3], np.float32)
+    th = np.deg2rad(35.0)
+    for q in ([1, 0, 0, 0], [np.cos(th / 2), 0, np.sin(th / 2), 0], [np.cos(th / 2), np.sin(th / 2) * 0.6, 0, np.sin(th / 2) * 0.8]):
+        P0, s, o, col = np.array([0.05, -0.03, 2.0]), (0.15, 0.25), 0.7, np.array([0.2, 0.8, 0.5])
+        out = _ka_run([(P0, s, q, o, col)], cam, H, W, bg)
+        a, depth, n = _ka_surfel(P0, s, q, o, cam, H, W)
+        am = out["allmap"]
+        assert (a > 0).mean() > 0.05
+        assert np.abs(am[1] - a).max() < 2e-6
+        assert np.abs(out["color"] - (col[:, None, None] * a + bg[:, None, None] * (1 - a))).max() < 2e-6
+        assert np.abs(am[0] - a * depth).max() < 5e-6
+        assert np.abs(am[2:5] - a[None] * n[:, None, None]).max() < 2e-6
+        assert np.abs(am[5] - np.where(a > 0, depth, 0.0)).max() < 5e-6          # median depth: T = 1 > 0.5 at the only hit
+        assert np.abs(am[6]).max() == 0.0                                        # one layer has no distortion
+        # radius = ceil(3 sigma of the larger projected axis) for the fronto-parallel case
+        if q == [1, 0, 0, 0]:
+            f_px = W / (2 * cam[2])
+            assert int(out["radii"][0]) == int(np.ceil(3 * max(s) * f_px / P0[2]))
+
+
+def test_known_answer_two_layers_compositing_and_distortion():
+    """Two fronto-parallel surfels at different depths: front-to-back compositing of colour / depth / alpha, the median
+    depth rule (last hit whose incoming transmittance is above 0.5) and the distortion term
+    a1 a2 (1 - a1) (m2 - m1)^2 with m = far / (far - near) (1 - near / z), near 0.2, far 100."""
+    H = W = 48
+    cam = _ka_camera(H, W)
+    bg = np.array([0.05, 0.1, 0.0], np.float32)
+    A = (np.array([0.02, 0.01, 1.5]), (0.12, 0.12), [1, 0, 0, 0], 0.6, np.array([0.9, 0.1, 0.2]))
+    B = (np.array([-0.04, 0.03, 2.5]), (0.3, 0.2), [1, 0, 0, 0], 0.9, np.array([0.1, 0.7, 0.9]))
+    out = _ka_run([B, A], cam, H, W, bg)                     # given back to front: the oracle has to sort them
+    a1, z1, _ = _ka_surfel(A[0], A[1], A[2], A[3], cam, H, W)
+    a2, z2, _ = _ka_surfel(B[0], B[1], B[2], B[3], cam, H, W)
+    T1 = 1 - a1
+    am = out["allmap"]
+    col = A[4][:, None, None] * a1 + B[4][:, None, None] * a2 * T1 + bg[:, None, None] * T1 * (1 - a2)
+    assert np.abs(out["color"] - col).max() < 3e-6
+    assert np.abs(am[1] - (a1 + a2 * T1)).max() < 3e-6
+    assert np.abs(am[0] - (a1 * z1 + a2 * T1 * z2)).max() < 1e-5
+    median = np.where((a2 > 0) & (T1 > 0.5), z2, np.where(a1 > 0, z1, 0.0))
+    assert np.abs(am[5] - median).max() < 1e-5
+    m = lambda z: 100.0 / (100.0 - 0.2) * (1 - 0.2 / z)
+    dist = a1 * a2 * T1 * (m(z2) - m(z1)) ** 2
+    assert np.abs(am[6] - dist).max() < 3e-6 and dist.max() > 1e-4
