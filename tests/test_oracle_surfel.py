@@ -107,11 +107,14 @@ def _ka_rot(q):
 
 
 def _ka_surfel(P0, s, q, o, cam, H, W):
+    return _ka_surfel_frame(P0, s, _ka_rot(q), o, cam, H, W)
+
+
+def _ka_surfel_frame(P0, s, R, o, cam, H, W):
     """Ray / plane intersection of every pixel's ray with the surfel's plane, local (u, v) in units of the scales, the
     2DGS low-pass (rho2d = 2 |pixel - box centre|^2), alpha = min(0.99, o exp(-min(rho3d, rho2d) / 2)) dropped below
     1/255, depth = hit depth (centre depth where the low-pass wins), normal turned towards the camera."""
     _, _, tanfov, px, py, dx, dy = cam
-    R = _ka_rot(q)
     tu, tv, n = R[:, 0], R[:, 1], R[:, 2]
     d = np.stack([dx, dy, np.ones_like(dx)], -1)
     t = (P0 @ n) / (d @ n)
@@ -189,3 +192,31 @@ def test_known_answer_two_layers_compositing_and_distortion():
     m = lambda z: 100.0 / (100.0 - 0.2) * (1 - 0.2 / z)
     dist = a1 * a2 * T1 * (m(z2) - m(z1)) ** 2
     assert np.abs(am[6] - dist).max() < 3e-6 and dist.max() > 1e-4
+
+
+def test_known_answer_orbit_camera_conventions():
+    """The same closed form under a look-at camera in the reference's 25-float pose layout (c2w + normalised K): the
+    row-vector view / projection matrices, the view-space normal and depth are what a plain w2c transform gives."""
+    from tools import synth
+    H = W = 64
+    pose = synth.orbit_pose25(40.0, 25.0, radius=2.2, fx=1.2)
+    view, proj, _, tanfov = synth.camera_from_pose25(pose)
+    w2c = np.linalg.inv(pose[:16].reshape(4, 4).astype(np.float64))
+    py, px = np.mgrid[0:H, 0:W].astype(np.float64)
+    cam = (view, proj, tanfov, px, py, ((2 * px + 1) / W - 1) * tanfov, ((2 * py + 1) / H - 1) * tanfov)
+    th = np.deg2rad(50.0)
+    q = np.array([np.cos(th / 2), 0.3 * np.sin(th / 2), np.sqrt(1 - 0.09 - 0.16) * np.sin(th / 2), 0.4 * np.sin(th / 2)])
+    Pw, s, o, col = np.array([0.08, -0.05, 0.1]), (0.2, 0.12), 0.85, np.array([0.6, 0.4, 0.9])
+    bg = np.zeros(3, np.float32)
+    out = so.rasterize(Pw[None].astype(np.float32), np.array([o], np.float32), np.array([s], np.float32),
+                       q[None].astype(np.float32), col[None].astype(np.float32), view, proj, bg, H, W)
+    # camera-space surfel: centre and frame through w2c, then the camera-at-origin closed form
+    Pc = w2c[:3, :3] @ Pw + w2c[:3, 3]
+    Rc = w2c[:3, :3] @ _ka_rot(q)
+    a, depth, n = _ka_surfel_frame(Pc, s, Rc, o, cam, H, W)
+    am = out["allmap"]
+    assert (a > 0).mean() > 0.03 and Pc[2] > 1.5
+    assert np.abs(am[1] - a).max() < 3e-6
+    assert np.abs(am[0] - a * depth).max() < 1e-5
+    assert np.abs(am[2:5] - a[None] * n[:, None, None]).max() < 3e-6
+    assert np.abs(out["color"] - col[:, None, None] * a).max() < 3e-6
