@@ -122,12 +122,23 @@ def _ka_surfel_frame(P0, s, R, o, cam, H, W):
     u, v = ((h - P0) @ tu) / s[0], ((h - P0) @ tv) / s[1]
     rho3 = u * u + v * v
     # upstream centres its screen-space low-pass on the centre of the bounding box of the projected 3-sigma ellipse
-    # (compute_aabb's `center`, not the projected splat centre): here from 40 000 projected boundary points
-    phi = np.linspace(0.0, 2 * np.pi, 40001)[:-1]
-    rim = P0[None] + 3.0 * (np.cos(phi)[:, None] * s[0] * tu[None] + np.sin(phi)[:, None] * s[1] * tv[None])
-    rx = ((rim[:, 0] / rim[:, 2] / tanfov + 1) * W - 1) * 0.5
-    ry = ((rim[:, 1] / rim[:, 2] / tanfov + 1) * H - 1) * 0.5
-    cx, cy = 0.5 * (rx.min() + rx.max()), 0.5 * (ry.min() + ry.max())
+    # (compute_aabb's `center`, not the projected splat centre): here the extremes of the projected rim, located on a
+    # 2 000-point sweep and polished by bounded scalar minimisation (no use of the oracle's quadric formula)
+    from scipy.optimize import minimize_scalar
+
+    def rim_pix(phi, axis):
+        r = P0 + 3.0 * (np.cos(phi) * s[0] * tu + np.sin(phi) * s[1] * tv)
+        return ((r[axis] / r[2] / tanfov + 1) * (W if axis == 0 else H) - 1) * 0.5
+
+    def extreme(axis, sign):
+        grid = np.linspace(0.0, 2 * np.pi, 2001)[:-1]
+        k = int(np.argmin([sign * rim_pix(p, axis) for p in grid]))
+        step = grid[1] - grid[0]
+        r = minimize_scalar(lambda p: sign * rim_pix(p, axis), bounds=(grid[k] - step, grid[k] + step), method="bounded",
+                            options={"xatol": 1e-13})
+        return rim_pix(r.x, axis)
+    cx = 0.5 * (extreme(0, 1.0) + extreme(0, -1.0))
+    cy = 0.5 * (extreme(1, 1.0) + extreme(1, -1.0))
     rho2 = 2.0 * ((px - cx) ** 2 + (py - cy) ** 2)
     depth = np.where(rho3 <= rho2, h[..., 2], P0[2])
     a = np.minimum(0.99, o * np.exp(-0.5 * np.minimum(rho3, rho2)))
@@ -220,3 +231,91 @@ def test_known_answer_orbit_camera_conventions():
     assert np.abs(am[0] - a * depth).max() < 1e-5
     assert np.abs(am[2:5] - a[None] * n[:, None, None]).max() < 3e-6
     assert np.abs(out["color"] - col[:, None, None] * a).max() < 3e-6
+
+
+def _ka_render(params, cam, H, W, bg):
+    """Closed-form image of K surfels (params [K, 13] = xyz, opacity, scales, quaternion, rgb; float64): every surfel's
+    alpha / depth / normal field from _ka_surfel_frame, composited front to back in the order of the centres' depths,
+    with the seven auxiliary channels as the reference consumes them (nsr/gs_surfel.py:121-163: [0] sum w z, [1] sum w,
+    [2:5] sum w n, [5] median depth, [6] distortion)."""
+    order = np.argsort(params[:, 2], kind="stable")
+    T = np.ones((H, W))
+    color = np.zeros((3, H, W))
+    am = np.zeros((7, H, W))
+    A = np.zeros((H, W)); M1 = np.zeros((H, W)); M2 = np.zeros((H, W))
+    for k in order:
+        p = params[k]
+        a, z, n = _ka_surfel_frame(p[0:3], p[4:6], _ka_rot(p[6:10]), p[3], cam, H, W)
+        w = a * T
+        m = 100.0 / (100.0 - 0.2) * (1 - 0.2 / np.where(z > 0, z, 1.0))
+        am[6] += (m * m * A + M2 - 2 * m * M1) * w
+        A += w; M1 += m * w; M2 += m * m * w
+        color += p[10:13][:, None, None] * w
+        am[0] += w * z
+        am[1] += w
+        am[2:5] += n[:, None, None] * w
+        am[5] = np.where((a > 0) & (T > 0.5), z, am[5])
+        T = T * (1 - a)
+    return color + bg[:, None, None] * T, am
+
+
+def test_known_answer_gradients_by_finite_differences():
+    """Analytic backward of the oracle against central differences (float64) of the independent closed form above:
+    three surfels -- a tilted one, a larger one behind it, and one that is smaller than a pixel so that the
+    screen-space low-pass and its bounding-box centre carry the gradient -- all 13 parameters of each.  The quaternion
+    gradient is compared in both variants (1: chained through the normalisation = the derivative of the closed form;
+    0: upstream's vjp at q/|q|, equal to it after projecting out the radial component)."""
+    H = W = 40
+    cam = _ka_camera(H, W)
+    bg = np.array([0.2, 0.1, 0.3])
+    th1, th2, th3 = np.deg2rad(30.0), np.deg2rad(-20.0), np.deg2rad(40.0)
+    params = np.array([
+        [0.03, -0.02, 1.6, 0.75, 0.16, 0.10, np.cos(th1 / 2), 0.0, np.sin(th1 / 2), 0.0, 0.9, 0.2, 0.1],
+        [-0.05, 0.04, 2.4, 0.90, 0.30, 0.22, np.cos(th2 / 2), np.sin(th2 / 2) * 0.6, np.sin(th2 / 2) * 0.8, 0.0, 0.1, 0.8, 0.6],
+        [0.10, 0.12, 2.0, 0.95, 0.008, 0.011, np.cos(th3 / 2), np.sin(th3 / 2) * 0.8, np.sin(th3 / 2) * 0.6, 0.0, 0.5, 0.5, 1.0]], np.float64)
+    rng = np.random.default_rng(5)
+    wc = rng.standard_normal((3, H, W))
+    wa = rng.standard_normal((7, H, W))
+    wa[5] = 0.0                                          # the median depth is piecewise constant in every parameter
+
+    def loss(p):
+        c, am = _ka_render(p, cam, H, W, bg)
+        return float((wc * c).sum() + (wa * am).sum())
+
+    fd = np.zeros_like(params)
+    for i in range(params.shape[0]):
+        for j in range(13):
+            e = np.zeros_like(params)
+            e[i, j] = 1e-6
+            fd[i, j] = (loss(params + e) - loss(params - e)) / 2e-6
+
+    def oracle_grads(variant):
+        rf, qn = so.get_variant()
+        so.set_variant(rf, variant)
+        try:
+            f32 = params.astype(np.float32)
+            fwd = so.rasterize(f32[:, 0:3], f32[:, 3], f32[:, 4:6], f32[:, 6:10], f32[:, 10:13], cam[0], cam[1],
+                               bg.astype(np.float32), H, W)
+            c, am = _ka_render(params, cam, H, W, bg)
+            assert np.abs(fwd["color"] - c).max() < 5e-6 and np.abs(fwd["allmap"][[0, 1, 2, 3, 4, 6]] - am[[0, 1, 2, 3, 4, 6]]).max() < 1e-5
+            return so.rasterize_backward(fwd, wc.astype(np.float32), wa.astype(np.float32))
+        finally:
+            so.set_variant(rf, qn)
+
+    TOL = 1e-4                                           # measured: 1e-7 .. 3e-6
+
+    def relerr(a, b):
+        return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
+
+    g1 = oracle_grads(1)
+    for name, sl in (("means3D", slice(0, 3)), ("opacities", slice(3, 4)), ("scales", slice(4, 6)), ("rotations", slice(6, 10)),
+                     ("colors", slice(10, 13))):
+        for i in range(params.shape[0]):
+            assert relerr(g1[name][i], fd[i, sl]) < TOL, (name, i, g1[name][i], fd[i, sl])
+    g0 = oracle_grads(0)
+    for i in range(params.shape[0]):
+        q = params[i, 6:10]                              # unit quaternions: the two variants differ by the radial part only
+        assert relerr(g0["rotations"][i] - q * (q @ g0["rotations"][i]), fd[i, 6:10]) < TOL
+        assert relerr(g0["means3D"][i], fd[i, 0:3]) < TOL
+    # the sub-pixel surfel really is in the low-pass regime: its position gradient is not negligible
+    assert np.linalg.norm(fd[2, 0:3]) > 1e-2
