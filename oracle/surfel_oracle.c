@@ -19,7 +19,11 @@
  *   /root/reference/nsr/lsgm/flow_matching_trainer.py:2174-2228 (camera layout)
  *   /root/reference/utils/gs_utils/graphics_utils.py:38-85      (projection)
  * Gradients are cross-checked against fp64 autograd of an independent torch
- * restatement (oracle/surfel_torch.py) in tests/test_oracle_surfel.py.
+ * restatement (oracle/surfel_torch.py) in tests/test_oracle_surfel.py; forward
+ * and backward are also checked there against closed-form ray / plane geometry
+ * and its float64 finite differences (test_known_answer_*), which pins that
+ * this file computes what the remembered conventions say -- not that the
+ * conventions are upstream's: the status stays "parity unpinned".
  *
  * Canonical arithmetic: every float op in the per-surfel stage (so_preprocess)
  * is a single IEEE-754 binary32 operation evaluated left to right with NO
